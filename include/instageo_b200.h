@@ -1,0 +1,166 @@
+/*
+ * instageo_b200.h -- C ABI of libinstageo_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for InstaGeo's chip-inference hot path.  The reference has no FFI
+ * layer (it is pure Python over PyTorch); every entry point below cites the reference
+ * Python interface it replaces (paths relative to the reference repo root).  The Python
+ * host mirror that binds these with ctypes lives in
+ * instageo-e2e-geospatial-ml_b200/_lib.py; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every data pointer is a DEVICE pointer owned by the caller (PyTorch allocates);
+ *     the library owns only the opaque ig_model (packed bf16 weights).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden
+ *     streams, no device-wide synchronisation in the forward path (CUDA-graph capturable).
+ *   - return 0 on success, negative IG_E* on failure; ig_last_error() gives a
+ *     thread-local message.  Never aborts, never prints.
+ *   - no CPU fallback: on a device that is not compute capability 10.x every compute
+ *     entry point returns IG_EARCH.
+ */
+#ifndef INSTAGEO_B200_H
+#define INSTAGEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IG_OK 0
+#define IG_EINVAL (-1)  /* bad argument */
+#define IG_ESHAPE (-2)  /* unsupported / inconsistent shape */
+#define IG_ECUDA (-3)   /* CUDA runtime or driver error */
+#define IG_ENOMEM (-4)  /* allocation failed / workspace too small */
+#define IG_EARCH (-5)   /* device is not sm_100 */
+#define IG_ESTATE (-6)  /* call order violated (e.g. forward before finalize) */
+
+/* element types of caller buffers */
+#define IG_F32 0
+#define IG_BF16 1
+#define IG_I16 2
+#define IG_U16 3
+#define IG_F64 4 /* ig_preprocess raw input only: already-scaled float64 host arrays */
+
+/* masking strategies, instageo/data/data_pipeline.py:254-267 */
+#define IG_MASK_EACH 0
+#define IG_MASK_ANY 1
+
+int ig_version(void);
+const char* ig_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernel 1: fused raster -> chip preprocessing.
+ * Replaces, per chip / window:
+ *   get_raster_data band gather            instageo/model/dataloader.py:700-703
+ *   arr_x * constant_multiplier (float64)  instageo/model/dataloader.py:741
+ *   arr_x == no_data_value                 instageo/model/dataloader.py:899
+ *   process_and_augment(crop=False) ->
+ *   normalize_and_convert_to_tensor        instageo/model/dataloader.py:495-524, 527-585
+ *   process_test window crops              instageo/model/dataloader.py:618-669
+ *   apply_mask / decode_fmask_value        instageo/data/data_pipeline.py:229-267,
+ *                                          instageo/data/hls_utils.py:77-86
+ *
+ * raw        [n_img, n_src_bands, H, W] int16|uint16 (or f32|f64, the reference's post-multiply
+ *            arrays) selected by raw_dtype, strides in ELEMENTS:
+ *            img_stride, band_stride, row_stride (pixel stride is 1).
+ * band_idx   [T*C] int32 (device) : source band of output (t, c) = band_idx[t*C + c].
+ * win_yx     [n_win, 3] int32 (device): (image index, top, left) of each win x win window;
+ *            NULL => n_win = n_img whole images with H == W == win.
+ * out_f32    [n_win, C, T, win, win] float32 or NULL          (reference layout)
+ * out_patch  [n_win*T*(win/16)^2, C*256] bf16 or NULL        (tubelet rows for kernel 2)
+ * mask_elem  [n_win, T*C, win, win] uint8 or NULL  : f64(raw)*cm == no_data_value
+ * mask_px    [n_win, win, win] uint8 or NULL       : OR of mask_elem over T*C
+ * fmask      [n_img, T, H, W] uint8 or NULL (same H/W geometry, dense); bits in fmask_bits
+ *            (bit p set => decode position p) mark pixels that are replaced by
+ *            no_data_value BEFORE scaling (strategy each|any).
+ * mean/std   [C] float32 (device).
+ */
+int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_src_bands, int H, int W,
+                  int64_t img_stride, int64_t band_stride, int64_t row_stride,
+                  const int32_t* band_idx, int T, int C, const int32_t* win_yx, int n_win, int win,
+                  double constant_multiplier, const float* mean, const float* std, int has_nodata,
+                  double no_data_value, const uint8_t* fmask, uint32_t fmask_bits,
+                  int masking_strategy, float* out_f32, void* out_patch, uint8_t* mask_elem,
+                  uint8_t* mask_px, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernel 5: overlap-averaging stitch of sliding-window logits (specification: SURVEY.md
+ * Appendix A.6; the reference snapshot only has the window grid, dataloader.py:655-664, the
+ * per-chip argmax, infer_utils.py:96-101, and a non-overlapping gdal_merge mosaic,
+ * instageo/new_apps/backend/app/cog_converter.py:122-134).
+ *
+ * win_logits [n_win, nc, win, win] float32; ys [ny], xs [nx] int32 (device) sorted window
+ * origins, window (iy, ix) is entry iy*nx + ix - win_base of win_logits (windows outside
+ * [win_base, win_base + n_win) must not cover rows [y0, y1)).
+ * Output rows [y0, y1) of the H x W tile: class_map [y1-y0, W] int8, optional avg
+ * [nc, y1-y0, W] float32, optional class histogram hist [nc+1] uint64 (last = nodata).
+ */
+int ig_stitch(const float* win_logits, int n_win, int win_base, int nc, int win,
+              const int32_t* ys, int ny, const int32_t* xs, int nx, int H, int W, int y0, int y1,
+              const uint8_t* nodata_px, int nodata_class, float* avg, int8_t* class_map,
+              unsigned long long* hist, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Kernels 2-4: PrithviSeg forward (instageo/model/model.py:292-419,
+ * instageo/model/pritvhi.py:370-530, timm==1.0.20 Block).
+ */
+typedef struct ig_model ig_model;
+
+typedef struct ig_model_cfg {
+  int embed_dim;    /* D: 768 | 1024 (256 for prithvi_eo_tiny) */
+  int depth;        /* encoder blocks */
+  int num_heads;    /* D / 64 */
+  int temporal;     /* T (num_frames) */
+  int num_classes;  /* 1 = regression head */
+  int img_size;     /* 224 */
+  int patch_size;   /* 16 */
+  int in_chans;     /* 6 */
+  int head_dims[5]; /* embed_dims of the segmentation head, model.py:380-383 */
+} ig_model_cfg;
+
+int ig_model_create(const ig_model_cfg* cfg, ig_model** out);
+/* key = state_dict key of the reference PrithviSeg ("prithvi_encoder.blocks.0.attn.qkv.weight",
+ * "segmentation_head.0.0.weight", ...); data = float32 DEVICE pointer, contiguous. Unknown
+ * keys that the reference forward never reads (e.g. *_embed_enc.scale, num_batches_tracked)
+ * return IG_OK and are ignored. */
+int ig_model_load_weight(ig_model* m, const char* key, const float* data, const int64_t* shape,
+                         int ndim, void* stream);
+/* bf16 repack, BatchNorm fold, ConvTranspose phase split, channel permutation. */
+int ig_model_finalize(ig_model* m, void* stream);
+size_t ig_model_workspace_bytes(const ig_model* m, int batch);
+/* x: [B, C, T, 224, 224] float32 (x_dtype IG_F32), or tubelet rows written by
+ * ig_preprocess(out_patch) (x_dtype IG_BF16).  logits [B, nc, 224, 224] float32 or NULL;
+ * argmax [B, 224, 224] int8 or NULL; feats [B, D*T, 14, 14] float32 or NULL. */
+int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits,
+                     int8_t* argmax, float* feats, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* number of kernel launches one ig_model_forward enqueues (for bench accounting) */
+int ig_model_launches_per_forward(const ig_model* m);
+/* debug / parity taps: copy an intermediate activation of the LAST forward as float32.
+ * name: "embed", "block<i>", "tokens", "convt<i>", "stage<i>".  dst layouts follow the
+ * oracle taps ([B,N,D] for tokens, [B,C,H,W] for head maps). */
+int ig_model_debug_tap(ig_model* m, const char* name, int batch, void* workspace, float* dst,
+                       size_t dst_elems, void* stream);
+int ig_model_destroy(ig_model* m);
+
+/* ---------------------------------------------------------------------------------------
+ * Building blocks exposed for parity tests and benchmarks (same kernels the model uses).
+ */
+/* out = epilogue(A[M,K] * W[N,K]^T + bias); A, W bf16 row-major; bias f32 or NULL.
+ * act: 0 none, 1 GELU(erf).  out_dtype IG_BF16 | IG_F32.  If resid != NULL (f32 [M,N]) it is
+ * added (out_dtype must be IG_F32; out may alias resid). */
+int ig_linear(const void* A, const void* W, const float* bias, const float* resid, void* out,
+              int out_dtype, int M, int N, int K, int act, void* stream);
+/* x f32 [M, D] -> bf16 [M, D], eps 1e-5 */
+int ig_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int D,
+                 void* stream);
+/* qkv bf16 [B*N, 3*D] (timm layout: q | k | v, head-major inside) -> out bf16 [B*N, D] */
+int ig_attention(const void* qkv, void* out, int B, int N, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTAGEO_B200_H */

@@ -1,0 +1,442 @@
+// Kernels 2-4 core: persistent, warp-specialised tcgen05 GEMM with TMEM accumulators.
+//
+//   D[128 x block_n] (f32, TMEM) += A[128 x 64] (bf16, smem via TMA) * B[block_n x 64]^T
+//
+// Roles (320 threads, 1 CTA per SM):
+//   warp 0      TMA producer   : 4-stage ring of {A 16 KB, B <= 32 KB} tiles, 128-byte swizzle
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (UMMA 128 x block_n x 16),
+//                                commits free the smem stage / publish the accumulator
+//   warps 2-9   epilogue       : tcgen05.ld the accumulator (2 warps per TMEM lane quadrant,
+//                                interleaved 16-column chunks), fused epilogue, global stores
+// Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the
+// main loop of tile i+1.
+//
+// The same kernel runs the segmentation head as an implicit GEMM with NO im2col: activations
+// live in a zero-bordered "padded-flat" NHWC layout [B*(H+2)*(W+2), C], so a 3x3 tap (dy,dx)
+// is the SAME 2-D matrix shifted by dy*(W+2)+dx rows -- one TMA coordinate offset per tap
+// (Taps::a_off).  ConvTranspose2d(k3,s2,p1,op1) is four output-parity phases with 1/2/2/4
+// taps that scatter rows to (2y+a, 2x+b).
+//
+// Reference arithmetic being replaced: nn.Linear / nn.Conv3d / nn.ConvTranspose2d /
+// nn.Conv2d / nn.BatchNorm2d(eval) / nn.ReLU / nn.GELU / torch.argmax in
+// instageo/model/pritvhi.py:243-268, :526-527 (timm Block), instageo/model/model.py:349-390,
+// instageo/model/infer_utils.py:96-101.
+#include "ig_gemm.cuh"
+
+namespace gemm {
+
+constexpr int A_BYTES = BM * BK * 2;          // 16384
+constexpr int B_BYTES = MAX_BN * BK * 2;      // 32768 (reserved; block_n*128 used)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;               // 196608
+constexpr int SMEM_BARS = 128;                                // barriers + tmem ptr
+constexpr int SMEM_FINAL = MAX_BN * NCP * 4 + 2 * BM * NCP * 4;  // w1 + exchange
+constexpr int SMEM_TOTAL = 1024 + SMEM_MAIN + SMEM_BARS + SMEM_FINAL;
+
+struct RowInfo {
+  bool valid;      // row < M
+  bool interior;   // conv modes: not a border pixel
+  int img, yy, xx; // conv modes: padded coordinates
+  int64_t orow;    // output row (mode dependent)
+};
+
+template <int EPI>
+__device__ __forceinline__ RowInfo make_row(const Args& a, int r, int phase) {
+  RowInfo ri;
+  ri.valid = r < a.M;
+  ri.interior = false;
+  ri.img = ri.yy = ri.xx = 0;
+  ri.orow = r;
+  if (EPI == EPI_PATCH) {
+    const int b = r / a.tok_per_img, tok = r - b * a.tok_per_img;
+    ri.orow = static_cast<int64_t>(b) * a.ntok + 1 + tok;
+    ri.xx = tok;
+  } else if (EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) {
+    const int hw = a.Hp * a.Wp;
+    ri.img = r / hw;
+    const int rem = r - ri.img * hw;
+    ri.yy = rem / a.Wp;
+    ri.xx = rem - ri.yy * a.Wp;
+    ri.interior = ri.valid && ri.yy >= 1 && ri.yy <= a.Hp - 2 && ri.xx >= 1 && ri.xx <= a.Wp - 2;
+    if (EPI == EPI_CONV) {
+      ri.orow = static_cast<int64_t>(a.out_guard) + r;
+    } else if (EPI == EPI_CONVT) {
+      const int Hp2 = 2 * (a.Hp - 2) + 2, Wp2 = 2 * (a.Wp - 2) + 2;
+      ri.orow = static_cast<int64_t>(a.out_guard) + static_cast<int64_t>(ri.img) * Hp2 * Wp2 +
+                static_cast<int64_t>(2 * (ri.yy - 1) + a.phase_a[phase] + 1) * Wp2 +
+                (2 * (ri.xx - 1) + a.phase_b[phase] + 1);
+    }
+  }
+  return ri;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SMEM_MAIN);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* w1s = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_BARS);  // [N][NCP]
+  float* exch = w1s + MAX_BN * NCP;                                      // [2][BM][NCP]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_phase = a.num_m_tiles * a.num_n_tiles;
+  const int total_tiles = tiles_per_phase * a.num_phases;
+  const int kblocks_per_tap = (a.kc + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ig::tma_prefetch_desc(&tmA);
+    ig::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ig::mbar_init(&full[s], 1);
+      ig::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ig::mbar_init(&tfull[s], 1);
+      ig::mbar_init(&tempty[s], NUM_EPI_WARPS);
+    }
+    ig::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ig::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ig::tmem_relinquish();
+  }
+  if (EPI == EPI_FINAL) {
+    for (int i = threadIdx.x; i < a.N * NCP; i += THREADS) w1s[i] = a.w1[i];
+  }
+  ig::tc_fence_before();
+  __syncthreads();
+  ig::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      const uint32_t tx_bytes = A_BYTES + a.block_n * BK * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int phase = tile / tiles_per_phase;
+        const int rem = tile - phase * tiles_per_phase;
+        const int m0 = (rem / a.num_n_tiles) * BM;
+        const int n0 = (rem % a.num_n_tiles) * a.block_n;
+        const Taps& tp = a.taps[phase];
+        for (int t = 0; t < tp.n; ++t) {
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            ig::mbar_wait(&empty[stage], ph ^ 1);
+            ig::mbar_expect_tx(&full[stage], tx_bytes);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            ig::tma_load_2d(sa, &tmA, &full[stage], kb * BK, a.a_row_base + m0 + tp.a_off[t]);
+            ig::tma_load_2d(sa + A_BYTES, &tmB, &full[stage], tp.b_off[t] + kb * BK, n0);
+            if (++stage == STAGES) {
+              stage = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ig::umma_idesc_bf16(BM, a.block_n, 0, 0);
+      int stage = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int phase = tile / tiles_per_phase;
+        const Taps& tp = a.taps[phase];
+        ig::mbar_wait(&tempty[acc], acc_ph ^ 1);
+        ig::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * MAX_BN;
+        uint32_t accumulate = 0;
+        for (int t = 0; t < tp.n; ++t) {
+          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            ig::mbar_wait(&full[stage], ph);
+            ig::tc_fence_after();
+            const uint32_t sa = ig::smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t da = ig::umma_desc_sw128(sa, 1024, 16);
+            const uint64_t db = ig::umma_desc_sw128(sa + A_BYTES, 1024, 16);
+            const int krem = a.kc - kb * BK;
+            const int nmma = krem >= BK ? BK / 16 : krem / 16;
+            for (int k = 0; k < nmma; ++k) {
+              ig::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            ig::umma_commit(&empty[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              ph ^= 1;
+            }
+          }
+        }
+        ig::umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;       // which interleaved set of 16-column chunks
+    const int nchunks = a.block_n / 16;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    int tile_par = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int phase = tile / tiles_per_phase;
+      const int rem = tile - phase * tiles_per_phase;
+      const int m0 = (rem / a.num_n_tiles) * BM;
+      const int n0 = (rem % a.num_n_tiles) * a.block_n;
+      const int row_in_tile = quad * 32 + lane;
+      const int r = m0 + row_in_tile;
+      const RowInfo ri = make_row<EPI>(a, r, phase);
+
+      ig::mbar_wait(&tfull[acc], acc_ph);
+      ig::tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * MAX_BN;
+
+      float logit[NCP];
+      if (EPI == EPI_FINAL) {
+#pragma unroll
+        for (int k = 0; k < NCP; ++k) logit[k] = 0.f;
+      }
+
+      for (int ch = half; ch < nchunks; ch += 2) {
+        uint32_t vr[16];
+        ig::tmem_ld16(taddr0 + ch * 16, vr);
+        ig::tmem_ld_wait();
+        const int col = n0 + ch * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
+
+        if (EPI == EPI_BF16) {
+          if (ri.valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t = v[j] + (a.bias ? __ldg(a.bias + col + j) : 0.f);
+              v[j] = a.act ? ig::gelu_erf(t) : t;
+            }
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + ri.orow * a.ldo + col;
+            uint4 q0, q1;
+            q0.x = ig::pack_bf16(v[0], v[1]);   q0.y = ig::pack_bf16(v[2], v[3]);
+            q0.z = ig::pack_bf16(v[4], v[5]);   q0.w = ig::pack_bf16(v[6], v[7]);
+            q1.x = ig::pack_bf16(v[8], v[9]);   q1.y = ig::pack_bf16(v[10], v[11]);
+            q1.z = ig::pack_bf16(v[12], v[13]); q1.w = ig::pack_bf16(v[14], v[15]);
+            reinterpret_cast<uint4*>(o)[0] = q0;
+            reinterpret_cast<uint4*>(o)[1] = q1;
+          }
+        } else if (EPI == EPI_F32 || EPI == EPI_RESID || EPI == EPI_PATCH) {
+          if (ri.valid) {
+            float* o = static_cast<float*>(a.out) + ri.orow * a.ldo + col;
+            const float* rs = (EPI == EPI_RESID) ? a.resid + ri.orow * a.ldo + col : nullptr;
+            const float* ps = (EPI == EPI_PATCH) ? a.pos + static_cast<int64_t>(1 + ri.xx) * a.N + col : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float4 t = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+              if (a.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
+                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+              }
+              if (EPI == EPI_RESID) {
+                const float4 b = reinterpret_cast<const float4*>(rs)[j4];
+                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+              }
+              if (EPI == EPI_PATCH) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ps) + j4);
+                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+              }
+              reinterpret_cast<float4*>(o)[j4] = t;
+            }
+          }
+        } else if (EPI == EPI_CONV) {
+          if (ri.valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float t = fmaf(v[j], __ldg(a.bias + col + j), __ldg(a.shift + col + j));
+              v[j] = ri.interior ? fmaxf(t, 0.f) : 0.f;
+            }
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + ri.orow * a.ldo + col;
+            uint4 q0, q1;
+            q0.x = ig::pack_bf16(v[0], v[1]);   q0.y = ig::pack_bf16(v[2], v[3]);
+            q0.z = ig::pack_bf16(v[4], v[5]);   q0.w = ig::pack_bf16(v[6], v[7]);
+            q1.x = ig::pack_bf16(v[8], v[9]);   q1.y = ig::pack_bf16(v[10], v[11]);
+            q1.z = ig::pack_bf16(v[12], v[13]); q1.w = ig::pack_bf16(v[14], v[15]);
+            reinterpret_cast<uint4*>(o)[0] = q0;
+            reinterpret_cast<uint4*>(o)[1] = q1;
+          }
+        } else if (EPI == EPI_CONVT) {
+          if (ri.interior) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(a.bias + col + j);
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + ri.orow * a.ldo + col;
+            uint4 q0, q1;
+            q0.x = ig::pack_bf16(v[0], v[1]);   q0.y = ig::pack_bf16(v[2], v[3]);
+            q0.z = ig::pack_bf16(v[4], v[5]);   q0.w = ig::pack_bf16(v[6], v[7]);
+            q1.x = ig::pack_bf16(v[8], v[9]);   q1.y = ig::pack_bf16(v[10], v[11]);
+            q1.z = ig::pack_bf16(v[12], v[13]); q1.w = ig::pack_bf16(v[14], v[15]);
+            reinterpret_cast<uint4*>(o)[0] = q0;
+            reinterpret_cast<uint4*>(o)[1] = q1;
+          }
+        } else if (EPI == EPI_FINAL) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float act = fmaxf(fmaf(v[j], __ldg(a.bias + col + j), __ldg(a.shift + col + j)), 0.f);
+            const float4* w4 = reinterpret_cast<const float4*>(w1s + (col + j) * NCP);
+#pragma unroll
+            for (int k4 = 0; k4 < NCP / 4; ++k4) {
+              const float4 w = w4[k4];
+              logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
+              logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
+              logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
+              logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
+            }
+          }
+        }
+      }
+      // accumulator fully read -> hand the TMEM stage back to the MMA warp
+      ig::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ig::mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+
+      if (EPI == EPI_FINAL) {
+        float* ex = exch + (tile_par * BM + row_in_tile) * NCP;
+        if (half == 1) {
+#pragma unroll
+          for (int k4 = 0; k4 < NCP / 4; ++k4)
+            reinterpret_cast<float4*>(ex)[k4] =
+                make_float4(logit[4 * k4], logit[4 * k4 + 1], logit[4 * k4 + 2], logit[4 * k4 + 3]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+        if (half == 0 && ri.interior) {
+          const int H = a.Hp - 2, W = a.Wp - 2;
+          const int64_t px = static_cast<int64_t>(ri.yy - 1) * W + (ri.xx - 1);
+          float best = 0.f;
+          int bi = 0;
+#pragma unroll
+          for (int k = 0; k < NCP; ++k) {
+            if (k < a.nc) {
+              const float lv = logit[k] + ex[k] + __ldg(a.b1 + k);
+              if (a.logits) a.logits[(static_cast<int64_t>(ri.img) * a.nc + k) * H * W + px] = lv;
+              if (k == 0 || lv > best) {
+                best = lv;
+                bi = k;
+              }
+            }
+          }
+          if (a.argmax) a.argmax[static_cast<int64_t>(ri.img) * H * W + px] = static_cast<int8_t>(bi);
+        }
+        tile_par ^= 1;
+      }
+    }
+  }
+
+  ig::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ig::tc_fence_after();
+    ig::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+static int launch_epi(const Plan& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    IG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_TOTAL));
+    configured = true;
+  }
+  const int total = p.args.num_m_tiles * p.args.num_n_tiles * p.args.num_phases;
+  if (total <= 0) return IG_OK;
+  const int grid = total < ig_num_sms() ? total : ig_num_sms();
+  gemm_kernel<EPI><<<grid, THREADS, SMEM_TOTAL, stream>>>(p.tmA, p.tmB, p.args);
+  IG_CUDA_OK(cudaGetLastError());
+  return IG_OK;
+}
+
+int launch(const Plan& p, cudaStream_t stream) {
+  const Args& a = p.args;
+  IG_REQUIRE(a.block_n >= 16 && a.block_n <= MAX_BN && a.block_n % 16 == 0, IG_ESHAPE,
+             "gemm: block_n=%d must be a multiple of 16 in [16,256]", a.block_n);
+  IG_REQUIRE(a.kc >= 16 && a.kc % 16 == 0, IG_ESHAPE, "gemm: K per tap %d must be a multiple of 16", a.kc);
+  IG_REQUIRE(a.N % a.block_n == 0, IG_ESHAPE, "gemm: N=%d not a multiple of block_n=%d", a.N, a.block_n);
+  switch (p.epi) {
+    case EPI_BF16: return launch_epi<EPI_BF16>(p, stream);
+    case EPI_F32: return launch_epi<EPI_F32>(p, stream);
+    case EPI_RESID: return launch_epi<EPI_RESID>(p, stream);
+    case EPI_PATCH: return launch_epi<EPI_PATCH>(p, stream);
+    case EPI_CONV: return launch_epi<EPI_CONV>(p, stream);
+    case EPI_CONVT: return launch_epi<EPI_CONVT>(p, stream);
+    case EPI_FINAL:
+      IG_REQUIRE(a.num_n_tiles == 1 && a.nc <= NCP, IG_ESHAPE, "gemm: fused head needs one N tile and nc <= %d", NCP);
+      return launch_epi<EPI_FINAL>(p, stream);
+    default: break;
+  }
+  ig_set_error("gemm: unknown epilogue %d", p.epi);
+  return IG_EINVAL;
+}
+
+int pick_block_n(int N) {
+  // largest multiple of 16 that divides N and fits one UMMA (<= 256)
+  for (int bn = MAX_BN; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int M, int N, int K) {
+  IG_REQUIRE(M >= 1 && N >= 16 && K >= 16 && K % 16 == 0 && N % 16 == 0, IG_ESHAPE,
+             "linear: unsupported shape M=%d N=%d K=%d (N, K multiples of 16)", M, N, K);
+  IG_REQUIRE(lda % 8 == 0 && K % 8 == 0, IG_ESHAPE, "linear: row pitch must be a multiple of 8 elements");
+  Args& a = p->args;
+  a = Args{};
+  a.M = M;
+  a.N = N;
+  a.block_n = pick_block_n(N);
+  a.kc = K;
+  a.num_m_tiles = (M + BM - 1) / BM;
+  a.num_n_tiles = N / a.block_n;
+  a.num_phases = 1;
+  a.a_row_base = 0;
+  a.taps[0].n = 1;
+  a.taps[0].a_off[0] = 0;
+  a.taps[0].b_off[0] = 0;
+  a.ldo = N;
+  p->epi = epi;
+  IG_TRY(ig_make_tmap_bf16(&p->tmA, A, M, K, lda, BM, BK));
+  IG_TRY(ig_make_tmap_bf16(&p->tmB, W, N, K, K, a.block_n, BK));
+  return IG_OK;
+}
+
+}  // namespace gemm
+
+extern "C" int ig_linear(const void* A, const void* W, const float* bias, const float* resid,
+                         void* out, int out_dtype, int M, int N, int K, int act, void* stream) {
+  IG_TRY(ig_check_device());
+  IG_REQUIRE(A && W && out, IG_EINVAL, "ig_linear: null pointer");
+  IG_REQUIRE(out_dtype == IG_BF16 || out_dtype == IG_F32, IG_EINVAL, "ig_linear: bad out_dtype");
+  IG_REQUIRE(!(resid && out_dtype != IG_F32), IG_EINVAL, "ig_linear: residual needs f32 output");
+  IG_REQUIRE(!(act && out_dtype != IG_BF16), IG_EINVAL, "ig_linear: activation needs bf16 output");
+  gemm::Plan p;
+  const int epi = out_dtype == IG_BF16 ? gemm::EPI_BF16 : (resid ? gemm::EPI_RESID : gemm::EPI_F32);
+  IG_TRY(gemm::plan_linear(&p, epi, A, K, W, M, N, K));
+  p.args.bias = bias;
+  p.args.resid = resid;
+  p.args.act = act;
+  p.args.out = out;
+  return gemm::launch(p, static_cast<cudaStream_t>(stream));
+}

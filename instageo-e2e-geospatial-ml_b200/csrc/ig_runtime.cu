@@ -1,0 +1,85 @@
+// Host runtime glue: thread-local error string, device gate, TMA descriptor encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ig_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void ig_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* ig_last_error(void) { return g_err; }
+extern "C" int ig_version(void) { return 100; }  // 0.1.0
+
+int ig_check_device() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = IG_OK;
+  int dev = 0;
+  IG_CUDA_OK(cudaGetDevice(&dev));
+  if (dev == cached_dev) {
+    if (cached_rc != IG_OK) ig_set_error("device %d is not an sm_100 (B200) GPU", dev);
+    return cached_rc;
+  }
+  int major = 0, minor = 0;
+  IG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  IG_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  cached_dev = dev;
+  cached_rc = (major == 10 && minor == 0) ? IG_OK : IG_EARCH;
+  if (cached_rc != IG_OK)
+    ig_set_error("device %d has compute capability %d.%d; this library is sm_100a only", dev, major, minor);
+  return cached_rc;
+}
+
+int ig_num_sms() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != dev_cached) {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    dev_cached = dev;
+  }
+  return sms;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t row_pitch, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  IG_REQUIRE(enc != nullptr, IG_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  IG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IG_EINVAL, "TMA base %p not 16-byte aligned", base);
+  IG_REQUIRE((row_pitch * 2) % 16 == 0, IG_ESHAPE, "TMA row pitch %llu elements not 16-byte aligned",
+             static_cast<unsigned long long>(row_pitch));
+  IG_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols * 2 == 128, IG_ESHAPE,
+             "TMA box %ux%u unsupported (128-byte swizzle rows)", box_rows, box_cols);
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {row_pitch * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IG_REQUIRE(r == CUDA_SUCCESS, IG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)",
+             static_cast<int>(r), static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols));
+  return IG_OK;
+}

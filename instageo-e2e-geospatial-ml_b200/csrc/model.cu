@@ -1,0 +1,545 @@
+// PrithviSeg forward engine behind the C ABI: weight store + kernel schedule.
+//
+// Replaces instageo/model/model.py:392-419 (PrithviSeg.forward) and
+// instageo/model/pritvhi.py:498-530 (PrithviViT.forward) for inference (eval semantics:
+// Dropout = identity, BatchNorm running statistics).  The library owns only packed weights;
+// every activation lives in the caller's workspace.
+//
+// Data layout in HBM (per batch of B chips, N = 1 + T*196 tokens):
+//   patches bf16 [B*T*196, 1536]      tubelet rows (k = c*256 + kh*16 + kw, Conv3d weight order)
+//   x       f32  [B*N, D]             residual stream (kept f32 across all blocks)
+//   xn      bf16 [B*N, D]             LayerNorm output = A operand of qkv / fc1
+//   qkv     bf16 [B*N, 3D]            timm layout, read in place by the attention kernel
+//   att     bf16 [B*N, D]             attention output = A operand of proj
+//   hid     bf16 [B*N, 4D]            GELU(fc1) = A operand of fc2
+//   head    bf16 padded-flat NHWC     [guard + B*(H+2)*(W+2) + guard, C] per stage, zero border;
+//                                     stage-0 channels stored t*D + d (weights permuted to match)
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ig_gemm.cuh"
+#include "ig_ops.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct LayerW {
+  float *ln1g, *ln1b, *ln2g, *ln2b, *qkv_b, *proj_b, *fc1_b, *fc2_b;
+  bf16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+};
+struct StageW {
+  bf16 *ct_w, *cv_w;
+  float *ct_b, *cv_b, *bn_g, *bn_b, *bn_m, *bn_v, *scale, *shift;
+};
+
+struct Buf {
+  size_t off;       // byte offset in the workspace
+  int Hp, Wp, C;    // padded geometry (head buffers)
+  int guard;        // guard rows before/after
+  int64_t rows;     // total rows incl. guards
+};
+
+struct Layout {
+  size_t patches, x, xn, qkv, att, hid;
+  Buf in0, t[4], a[3];
+  size_t total;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct ig_model {
+  ig_model_cfg cfg;
+  int D, L, heads, T, nc, g, ntok, K0;
+  int dims[5];
+  int device;
+  bool finalized;
+  std::vector<void*> allocs;
+  std::vector<std::string> missing;  // required keys not loaded yet
+  // encoder
+  bf16* pe_w;
+  float *pe_b, *pos, *cls, *norm_g, *norm_b;
+  std::vector<LayerW> layers;
+  StageW st[4];
+  float *w1_raw, *b1_raw, *w1, *b1;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(ig_model* m, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+  if (e != cudaSuccess) {
+    ig_set_error("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return IG_ENOMEM;
+  }
+  m->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return IG_OK;
+}
+
+Buf make_buf(size_t* cur, int B, int H, int C) {
+  Buf b;
+  b.Hp = H + 2;
+  b.Wp = H + 2;
+  b.C = C;
+  b.guard = b.Wp + 8;
+  b.rows = static_cast<int64_t>(b.guard) * 2 + static_cast<int64_t>(B) * b.Hp * b.Wp;
+  b.off = *cur;
+  *cur = align_up(*cur + static_cast<size_t>(b.rows) * C * sizeof(bf16), 1024);
+  return b;
+}
+
+Layout make_layout(const ig_model* m, int B) {
+  Layout l;
+  size_t cur = 0;
+  const size_t rows = static_cast<size_t>(B) * m->ntok;
+  auto take = [&](size_t bytes) {
+    size_t o = cur;
+    cur = align_up(cur + bytes, 1024);
+    return o;
+  };
+  l.patches = take(static_cast<size_t>(B) * m->T * m->g * m->g * m->K0 * sizeof(bf16));
+  l.x = take(rows * m->D * sizeof(float));
+  l.xn = take(rows * m->D * sizeof(bf16));
+  l.qkv = take(rows * 3 * m->D * sizeof(bf16));
+  l.att = take(rows * m->D * sizeof(bf16));
+  l.hid = take(rows * 4 * m->D * sizeof(bf16));
+  l.in0 = make_buf(&cur, B, m->g, m->dims[0]);
+  int H = m->g;
+  for (int i = 0; i < 4; ++i) {
+    H *= 2;
+    l.t[i] = make_buf(&cur, B, H, m->dims[i + 1]);
+    if (i < 3) l.a[i] = make_buf(&cur, B, H, m->dims[i + 1]);
+  }
+  l.total = cur;
+  return l;
+}
+
+bool starts_with(const char* s, const char* p) { return strncmp(s, p, strlen(p)) == 0; }
+
+void mark_loaded(ig_model* m, const char* key) {
+  for (size_t i = 0; i < m->missing.size(); ++i)
+    if (m->missing[i] == key) {
+      m->missing.erase(m->missing.begin() + i);
+      return;
+    }
+}
+
+int64_t numel(const int64_t* shape, int ndim) {
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  return n;
+}
+
+int copy_f32(float* dst, const float* src, int64_t n, int64_t expect, const char* key, cudaStream_t st) {
+  IG_REQUIRE(n == expect, IG_ESHAPE, "weight %s has %lld elements, expected %lld", key,
+             static_cast<long long>(n), static_cast<long long>(expect));
+  IG_CUDA_OK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return IG_OK;
+}
+int copy_bf16(bf16* dst, const float* src, int64_t n, int64_t expect, const char* key, cudaStream_t st) {
+  IG_REQUIRE(n == expect, IG_ESHAPE, "weight %s has %lld elements, expected %lld", key,
+             static_cast<long long>(n), static_cast<long long>(expect));
+  return ops::cvt_bf16(src, dst, n, st);
+}
+
+}  // namespace
+
+extern "C" int ig_model_create(const ig_model_cfg* cfg, ig_model** out) {
+  IG_TRY(ig_check_device());
+  IG_REQUIRE(cfg && out, IG_EINVAL, "ig_model_create: null pointer");
+  IG_REQUIRE(cfg->patch_size == 16 && cfg->in_chans == 6, IG_ESHAPE,
+             "only patch_size 16 / 6 input bands are supported (got %d / %d); the V2-600M variants "
+             "(patch 14, head kernels 5/7) are out of scope", cfg->patch_size, cfg->in_chans);
+  IG_REQUIRE(cfg->img_size >= 16 && cfg->img_size % 16 == 0 && cfg->img_size <= 224, IG_ESHAPE,
+             "img_size %d unsupported", cfg->img_size);
+  IG_REQUIRE(cfg->embed_dim % 128 == 0 && cfg->embed_dim >= 128 && cfg->embed_dim <= 1024, IG_ESHAPE,
+             "embed_dim %d unsupported (multiple of 128, <= 1024)", cfg->embed_dim);
+  IG_REQUIRE(cfg->num_heads * 64 == cfg->embed_dim, IG_ESHAPE, "head_dim must be 64 (D=%d heads=%d)",
+             cfg->embed_dim, cfg->num_heads);
+  IG_REQUIRE(cfg->depth >= 0 && cfg->temporal >= 1 && cfg->temporal <= 8, IG_ESHAPE, "bad depth/temporal");
+  IG_REQUIRE(cfg->num_classes >= 1 && cfg->num_classes <= gemm::NCP, IG_ESHAPE, "num_classes %d unsupported (1..%d)",
+             cfg->num_classes, gemm::NCP);
+  IG_REQUIRE(cfg->head_dims[0] == cfg->embed_dim * cfg->temporal, IG_ESHAPE,
+             "head_dims[0]=%d must equal embed_dim*temporal=%d", cfg->head_dims[0], cfg->embed_dim * cfg->temporal);
+  for (int i = 0; i < 5; ++i)
+    IG_REQUIRE(cfg->head_dims[i] >= 16 && cfg->head_dims[i] % 16 == 0 && gemm::pick_block_n(cfg->head_dims[i]) > 0,
+               IG_ESHAPE, "head_dims[%d]=%d must be a multiple of 16", i, cfg->head_dims[i]);
+  IG_REQUIRE(cfg->head_dims[4] <= gemm::MAX_BN, IG_ESHAPE, "head_dims[4]=%d must be <= %d for the fused 1x1 head",
+             cfg->head_dims[4], gemm::MAX_BN);
+
+  ig_model* m = new ig_model();
+  m->cfg = *cfg;
+  m->D = cfg->embed_dim;
+  m->L = cfg->depth;
+  m->heads = cfg->num_heads;
+  m->T = cfg->temporal;
+  m->nc = cfg->num_classes;
+  m->g = cfg->img_size / 16;
+  m->ntok = 1 + m->T * m->g * m->g;
+  m->K0 = cfg->in_chans * 256;
+  for (int i = 0; i < 5; ++i) m->dims[i] = cfg->head_dims[i];
+  m->finalized = false;
+  cudaGetDevice(&m->device);
+  const int D = m->D;
+  int rc = IG_OK;
+#define A(ptr, n) if (rc == IG_OK) rc = dev_alloc(m, &(ptr), static_cast<size_t>(n))
+  A(m->pe_w, static_cast<size_t>(D) * m->K0);
+  A(m->pe_b, D);
+  A(m->pos, static_cast<size_t>(m->ntok) * D);
+  A(m->cls, D);
+  A(m->norm_g, D);
+  A(m->norm_b, D);
+  m->layers.resize(m->L);
+  for (int i = 0; i < m->L && rc == IG_OK; ++i) {
+    LayerW& w = m->layers[i];
+    A(w.ln1g, D); A(w.ln1b, D); A(w.ln2g, D); A(w.ln2b, D);
+    A(w.qkv_b, 3 * D); A(w.proj_b, D); A(w.fc1_b, 4 * D); A(w.fc2_b, D);
+    A(w.qkv_w, static_cast<size_t>(3) * D * D); A(w.proj_w, static_cast<size_t>(D) * D);
+    A(w.fc1_w, static_cast<size_t>(4) * D * D); A(w.fc2_w, static_cast<size_t>(4) * D * D);
+  }
+  for (int i = 0; i < 4 && rc == IG_OK; ++i) {
+    StageW& s = m->st[i];
+    const size_t ci = m->dims[i], co = m->dims[i + 1];
+    A(s.ct_w, 9 * ci * co); A(s.cv_w, 9 * co * co);
+    A(s.ct_b, co); A(s.cv_b, co); A(s.bn_g, co); A(s.bn_b, co); A(s.bn_m, co); A(s.bn_v, co);
+    A(s.scale, co); A(s.shift, co);
+  }
+  A(m->w1_raw, static_cast<size_t>(m->nc) * m->dims[4]);
+  A(m->b1_raw, m->nc);
+  A(m->w1, static_cast<size_t>(m->dims[4]) * gemm::NCP);
+  A(m->b1, gemm::NCP);
+#undef A
+  if (rc != IG_OK) {
+    ig_model_destroy(m);
+    return rc;
+  }
+  // required state_dict keys
+  auto need = [&](const std::string& k) { m->missing.push_back(k); };
+  const std::string e = "prithvi_encoder.";
+  need(e + "cls_token"); need(e + "pos_embed");
+  need(e + "patch_embed.proj.weight"); need(e + "patch_embed.proj.bias");
+  need(e + "norm.weight"); need(e + "norm.bias");
+  for (int i = 0; i < m->L; ++i) {
+    const std::string b = e + "blocks." + std::to_string(i) + ".";
+    for (const char* s : {"norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
+                          "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                          "mlp.fc2.weight", "mlp.fc2.bias"})
+      need(b + s);
+  }
+  for (int i = 0; i < 4; ++i) {
+    const std::string h = "segmentation_head." + std::to_string(i) + ".";
+    for (const char* s : {"0.weight", "0.bias", "2.weight", "2.bias", "3.weight", "3.bias", "3.running_mean",
+                          "3.running_var"})
+      need(h + s);
+  }
+  need("segmentation_head.5.weight");
+  need("segmentation_head.5.bias");
+  *out = m;
+  return IG_OK;
+}
+
+extern "C" int ig_model_destroy(ig_model* m) {
+  if (!m) return IG_OK;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return IG_OK;
+}
+
+extern "C" int ig_model_load_weight(ig_model* m, const char* key, const float* data, const int64_t* shape,
+                                    int ndim, void* stream) {
+  IG_REQUIRE(m && key && data && (shape || ndim == 0), IG_EINVAL, "ig_model_load_weight: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n = numel(shape, ndim);
+  const int D = m->D;
+  int rc = IG_OK;
+  bool known = true;
+  const char* e = "prithvi_encoder.";
+  if (starts_with(key, e)) {
+    const char* k = key + strlen(e);
+    if (!strcmp(k, "cls_token")) rc = copy_f32(m->cls, data, n, D, key, st);
+    else if (!strcmp(k, "pos_embed")) rc = copy_f32(m->pos, data, n, static_cast<int64_t>(m->ntok) * D, key, st);
+    else if (!strcmp(k, "patch_embed.proj.weight")) rc = copy_bf16(m->pe_w, data, n, static_cast<int64_t>(D) * m->K0, key, st);
+    else if (!strcmp(k, "patch_embed.proj.bias")) rc = copy_f32(m->pe_b, data, n, D, key, st);
+    else if (!strcmp(k, "norm.weight")) rc = copy_f32(m->norm_g, data, n, D, key, st);
+    else if (!strcmp(k, "norm.bias")) rc = copy_f32(m->norm_b, data, n, D, key, st);
+    else if (starts_with(k, "blocks.")) {
+      char* end = nullptr;
+      const long li = strtol(k + 7, &end, 10);
+      if (li < 0 || li >= m->L || !end || *end != '.') {
+        known = false;  // blocks beyond `depth` are dropped like model.py:242-247
+      } else {
+        LayerW& w = m->layers[li];
+        const char* s = end + 1;
+        const int64_t DD = static_cast<int64_t>(D) * D;
+        if (!strcmp(s, "norm1.weight")) rc = copy_f32(w.ln1g, data, n, D, key, st);
+        else if (!strcmp(s, "norm1.bias")) rc = copy_f32(w.ln1b, data, n, D, key, st);
+        else if (!strcmp(s, "norm2.weight")) rc = copy_f32(w.ln2g, data, n, D, key, st);
+        else if (!strcmp(s, "norm2.bias")) rc = copy_f32(w.ln2b, data, n, D, key, st);
+        else if (!strcmp(s, "attn.qkv.weight")) rc = copy_bf16(w.qkv_w, data, n, 3 * DD, key, st);
+        else if (!strcmp(s, "attn.qkv.bias")) rc = copy_f32(w.qkv_b, data, n, 3 * D, key, st);
+        else if (!strcmp(s, "attn.proj.weight")) rc = copy_bf16(w.proj_w, data, n, DD, key, st);
+        else if (!strcmp(s, "attn.proj.bias")) rc = copy_f32(w.proj_b, data, n, D, key, st);
+        else if (!strcmp(s, "mlp.fc1.weight")) rc = copy_bf16(w.fc1_w, data, n, 4 * DD, key, st);
+        else if (!strcmp(s, "mlp.fc1.bias")) rc = copy_f32(w.fc1_b, data, n, 4 * D, key, st);
+        else if (!strcmp(s, "mlp.fc2.weight")) rc = copy_bf16(w.fc2_w, data, n, 4 * DD, key, st);
+        else if (!strcmp(s, "mlp.fc2.bias")) rc = copy_f32(w.fc2_b, data, n, D, key, st);
+        else known = false;
+      }
+    } else {
+      known = false;  // temporal_embed_enc.* / location_embed_enc.*: never read by forward
+    }
+  } else if (starts_with(key, "segmentation_head.")) {
+    const char* k = key + strlen("segmentation_head.");
+    if (!strcmp(k, "5.weight")) rc = copy_f32(m->w1_raw, data, n, static_cast<int64_t>(m->nc) * m->dims[4], key, st);
+    else if (!strcmp(k, "5.bias")) rc = copy_f32(m->b1_raw, data, n, m->nc, key, st);
+    else if (k[0] >= '0' && k[0] <= '3' && k[1] == '.') {
+      const int i = k[0] - '0';
+      StageW& s = m->st[i];
+      const int ci = m->dims[i], co = m->dims[i + 1];
+      const char* r = k + 2;
+      if (!strcmp(r, "0.weight")) {
+        IG_REQUIRE(ndim == 4 && shape[0] == ci && shape[1] == co && shape[2] == 3 && shape[3] == 3, IG_ESHAPE,
+                   "%s: expected [%d,%d,3,3]", key, ci, co);
+        rc = ops::repack_conv_weight(data, s.ct_w, ci, co, 1, i == 0 ? m->T : 1, st);
+      } else if (!strcmp(r, "2.weight")) {
+        IG_REQUIRE(ndim == 4 && shape[0] == co && shape[1] == co && shape[2] == 3 && shape[3] == 3, IG_ESHAPE,
+                   "%s: expected [%d,%d,3,3] (head kernel sizes other than 3 are out of scope)", key, co, co);
+        rc = ops::repack_conv_weight(data, s.cv_w, co, co, 0, 1, st);
+      } else if (!strcmp(r, "0.bias")) rc = copy_f32(s.ct_b, data, n, co, key, st);
+      else if (!strcmp(r, "2.bias")) rc = copy_f32(s.cv_b, data, n, co, key, st);
+      else if (!strcmp(r, "3.weight")) rc = copy_f32(s.bn_g, data, n, co, key, st);
+      else if (!strcmp(r, "3.bias")) rc = copy_f32(s.bn_b, data, n, co, key, st);
+      else if (!strcmp(r, "3.running_mean")) rc = copy_f32(s.bn_m, data, n, co, key, st);
+      else if (!strcmp(r, "3.running_var")) rc = copy_f32(s.bn_v, data, n, co, key, st);
+      else known = false;
+    } else {
+      known = false;
+    }
+  } else {
+    known = false;
+  }
+  if (rc != IG_OK) return rc;
+  if (known) {
+    mark_loaded(m, key);
+    m->finalized = false;
+  }
+  return IG_OK;
+}
+
+extern "C" int ig_model_finalize(ig_model* m, void* stream) {
+  IG_REQUIRE(m, IG_EINVAL, "ig_model_finalize: null model");
+  if (!m->missing.empty()) {
+    ig_set_error("ig_model_finalize: %zu weights not loaded, first missing: %s", m->missing.size(),
+                 m->missing[0].c_str());
+    return IG_ESTATE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < 4; ++i) {
+    StageW& s = m->st[i];
+    IG_TRY(ops::bn_fold(s.bn_g, s.bn_b, s.bn_m, s.bn_v, s.cv_b, s.scale, s.shift, m->dims[i + 1], st));
+  }
+  IG_TRY(ops::repack_head1x1(m->w1_raw, m->b1_raw, m->w1, m->b1, m->nc, m->dims[4], gemm::NCP, st));
+  m->finalized = true;
+  return IG_OK;
+}
+
+extern "C" size_t ig_model_workspace_bytes(const ig_model* m, int batch) {
+  if (!m || batch < 1) return 0;
+  return make_layout(m, batch).total;
+}
+
+extern "C" int ig_model_launches_per_forward(const ig_model* m) {
+  if (!m) return 0;
+  // patchify + cls + patch-embed + 7 per block + final norm + 5 border clears + 8 head GEMMs
+  return 3 + 7 * m->L + 1 + 5 + 8;
+}
+
+namespace {
+
+int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in, const void* w, int Cin, int Cout,
+              int B, bool transposed) {
+  gemm::Args& a = p->args;
+  a = gemm::Args{};
+  a.M = B * in.Hp * in.Wp;
+  a.N = Cout;
+  a.block_n = gemm::pick_block_n(Cout);
+  a.kc = Cin;
+  a.num_m_tiles = (a.M + gemm::BM - 1) / gemm::BM;
+  a.num_n_tiles = Cout / a.block_n;
+  a.a_row_base = in.guard;
+  a.Hp = in.Hp;
+  a.Wp = in.Wp;
+  a.ldo = Cout;
+  if (!transposed) {
+    a.num_phases = 1;
+    a.taps[0].n = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        a.taps[0].a_off[ky * 3 + kx] = (ky - 1) * in.Wp + (kx - 1);
+        a.taps[0].b_off[ky * 3 + kx] = (ky * 3 + kx) * Cin;
+      }
+  } else {
+    // out[2y+pa, 2x+pb]: pa=0 -> (ky=1, dy=0); pa=1 -> (ky=2, dy=0), (ky=0, dy=1); same along x
+    a.num_phases = 4;
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        const int ph = pa * 2 + pb;
+        a.phase_a[ph] = pa;
+        a.phase_b[ph] = pb;
+        gemm::Taps& t = a.taps[ph];
+        t.n = 0;
+        const int kys[2] = {pa ? 2 : 1, 0}, dys[2] = {0, 1};
+        const int kxs[2] = {pb ? 2 : 1, 0}, dxs[2] = {0, 1};
+        for (int iy = 0; iy < (pa ? 2 : 1); ++iy)
+          for (int ix = 0; ix < (pb ? 2 : 1); ++ix) {
+            t.a_off[t.n] = dys[iy] * in.Wp + dxs[ix];
+            t.b_off[t.n] = (kys[iy] * 3 + kxs[ix]) * Cin;
+            ++t.n;
+          }
+      }
+  }
+  p->epi = epi;
+  IG_TRY(ig_make_tmap_bf16(&p->tmA, ws + in.off, in.rows, Cin, Cin, gemm::BM, gemm::BK));
+  IG_TRY(ig_make_tmap_bf16(&p->tmB, w, Cout, 9 * static_cast<uint64_t>(Cin), 9 * static_cast<uint64_t>(Cin),
+                           a.block_n, gemm::BK));
+  (void)m;
+  return IG_OK;
+}
+
+}  // namespace
+
+extern "C" int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits, int8_t* argmax,
+                                float* feats, void* workspace, size_t workspace_bytes, void* stream) {
+  IG_TRY(ig_check_device());
+  IG_REQUIRE(m && x && workspace, IG_EINVAL, "ig_model_forward: null pointer");
+  IG_REQUIRE(m->finalized, IG_ESTATE, "ig_model_forward: call ig_model_finalize after loading weights");
+  IG_REQUIRE(batch >= 1, IG_ESHAPE, "ig_model_forward: batch %d", batch);
+  IG_REQUIRE(x_dtype == IG_F32 || x_dtype == IG_BF16, IG_EINVAL, "ig_model_forward: x_dtype must be IG_F32 or IG_BF16");
+  IG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, IG_EINVAL, "workspace must be 1024-byte aligned");
+  const Layout l = make_layout(m, batch);
+  IG_REQUIRE(workspace_bytes >= l.total, IG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, l.total);
+  IG_REQUIRE(static_cast<int64_t>(batch) * (226 * 226) < (1ll << 31) - 4096, IG_ESHAPE, "batch %d too large", batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const int B = batch, D = m->D, T = m->T, g = m->g, N = m->ntok;
+  const int M = B * N, MP = B * T * g * g;
+  float* xres = reinterpret_cast<float*>(ws + l.x);
+  bf16* xn = reinterpret_cast<bf16*>(ws + l.xn);
+  bf16* qkv = reinterpret_cast<bf16*>(ws + l.qkv);
+  bf16* att = reinterpret_cast<bf16*>(ws + l.att);
+  bf16* hid = reinterpret_cast<bf16*>(ws + l.hid);
+
+  // ---- kernel 2: tubelet patch embedding (im2col-free: rows are written once, in GEMM order)
+  const void* patches = x;
+  if (x_dtype == IG_F32) {
+    IG_TRY(ops::patchify(static_cast<const float*>(x), ws + l.patches, B, m->cfg.in_chans, T, m->cfg.img_size, st));
+    patches = ws + l.patches;
+  }
+  IG_TRY(ops::init_cls(xres, m->cls, m->pos, B, N, D, st));
+  gemm::Plan p;
+  IG_TRY(gemm::plan_linear(&p, gemm::EPI_PATCH, patches, m->K0, m->pe_w, MP, D, m->K0));
+  p.args.bias = m->pe_b;
+  p.args.pos = m->pos;
+  p.args.tok_per_img = T * g * g;
+  p.args.ntok = N;
+  p.args.out = xres;
+  IG_TRY(gemm::launch(p, st));
+
+  // ---- kernel 3: encoder blocks
+  for (int i = 0; i < m->L; ++i) {
+    const LayerW& w = m->layers[i];
+    IG_TRY(ops::layernorm(xres, w.ln1g, w.ln1b, xn, M, D, 0, 0, 0, 0, 0, st));
+    IG_TRY(gemm::plan_linear(&p, gemm::EPI_BF16, xn, D, w.qkv_w, M, 3 * D, D));
+    p.args.bias = w.qkv_b;
+    p.args.out = qkv;
+    IG_TRY(gemm::launch(p, st));
+    IG_TRY(ops::attention(qkv, att, B, N, m->heads, st));
+    IG_TRY(gemm::plan_linear(&p, gemm::EPI_RESID, att, D, w.proj_w, M, D, D));
+    p.args.bias = w.proj_b;
+    p.args.resid = xres;
+    p.args.out = xres;
+    IG_TRY(gemm::launch(p, st));
+    IG_TRY(ops::layernorm(xres, w.ln2g, w.ln2b, xn, M, D, 0, 0, 0, 0, 0, st));
+    IG_TRY(gemm::plan_linear(&p, gemm::EPI_BF16, xn, D, w.fc1_w, M, 4 * D, D));
+    p.args.bias = w.fc1_b;
+    p.args.act = 1;
+    p.args.out = hid;
+    IG_TRY(gemm::launch(p, st));
+    IG_TRY(gemm::plan_linear(&p, gemm::EPI_RESID, hid, 4 * D, w.fc2_w, M, D, 4 * D));
+    p.args.bias = w.fc2_b;
+    p.args.resid = xres;
+    p.args.out = xres;
+    IG_TRY(gemm::launch(p, st));
+  }
+
+  // ---- final norm, written straight into the head's padded-flat input (cls dropped)
+  IG_TRY(ops::zero_ring(ws + l.in0.off + static_cast<size_t>(l.in0.guard) * l.in0.C * 2, B, l.in0.Hp, l.in0.Wp,
+                        l.in0.C, st));
+  IG_TRY(ops::layernorm(xres, m->norm_g, m->norm_b, ws + l.in0.off, M, D, 1, N, T, g, l.in0.guard, st));
+  if (feats)
+    IG_TRY(ops::unpad_to_nchw(ws + l.in0.off, feats, B, l.in0.Hp, l.in0.Wp, l.in0.C, l.in0.guard, T, st));
+
+  // ---- kernel 4: segmentation head
+  const Buf* in = &l.in0;
+  for (int i = 0; i < 4; ++i) {
+    const StageW& s = m->st[i];
+    const Buf& tb = l.t[i];
+    IG_TRY(ops::zero_ring(ws + tb.off + static_cast<size_t>(tb.guard) * tb.C * 2, B, tb.Hp, tb.Wp, tb.C, st));
+    IG_TRY(plan_conv(&p, gemm::EPI_CONVT, m, ws, *in, s.ct_w, m->dims[i], m->dims[i + 1], B, true));
+    p.args.bias = s.ct_b;
+    p.args.out = ws + tb.off;
+    p.args.out_guard = tb.guard;
+    IG_TRY(gemm::launch(p, st));
+    if (i < 3) {
+      const Buf& ab = l.a[i];
+      IG_TRY(plan_conv(&p, gemm::EPI_CONV, m, ws, tb, s.cv_w, m->dims[i + 1], m->dims[i + 1], B, false));
+      p.args.bias = s.scale;
+      p.args.shift = s.shift;
+      p.args.out = ws + ab.off;
+      p.args.out_guard = ab.guard;
+      IG_TRY(gemm::launch(p, st));
+      in = &ab;
+    } else {
+      IG_TRY(plan_conv(&p, gemm::EPI_FINAL, m, ws, tb, s.cv_w, m->dims[4], m->dims[4], B, false));
+      p.args.bias = s.scale;
+      p.args.shift = s.shift;
+      p.args.w1 = m->w1;
+      p.args.b1 = m->b1;
+      p.args.nc = m->nc;
+      p.args.logits = logits;
+      p.args.argmax = (m->nc > 1) ? argmax : nullptr;
+      IG_TRY(gemm::launch(p, st));
+    }
+  }
+  return IG_OK;
+}
+
+extern "C" int ig_model_debug_tap(ig_model* m, const char* name, int batch, void* workspace, float* dst,
+                                  size_t dst_elems, void* stream) {
+  IG_REQUIRE(m && name && workspace && dst, IG_EINVAL, "ig_model_debug_tap: null pointer");
+  const Layout l = make_layout(m, batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  if (!strcmp(name, "x")) {  // residual stream after the last block, [B, N, D]
+    const size_t n = static_cast<size_t>(batch) * m->ntok * m->D;
+    IG_REQUIRE(dst_elems >= n, IG_ENOMEM, "tap x needs %zu elements", n);
+    IG_CUDA_OK(cudaMemcpyAsync(dst, ws + l.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return IG_OK;
+  }
+  const Buf* b = nullptr;
+  int permT = 1;
+  if (!strcmp(name, "feat")) { b = &l.in0; permT = m->T; }
+  else if (starts_with(name, "convt") && name[5] >= '0' && name[5] <= '3') b = &l.t[name[5] - '0'];
+  else if (starts_with(name, "stage") && name[5] >= '0' && name[5] <= '2') b = &l.a[name[5] - '0'];
+  IG_REQUIRE(b != nullptr, IG_EINVAL, "unknown tap '%s' (x, feat, convt0-3, stage0-2)", name);
+  const size_t n = static_cast<size_t>(batch) * b->C * (b->Hp - 2) * (b->Wp - 2);
+  IG_REQUIRE(dst_elems >= n, IG_ENOMEM, "tap %s needs %zu elements", name, n);
+  return ops::unpad_to_nchw(ws + b->off, dst, batch, b->Hp, b->Wp, b->C, b->guard, permT, st);
+}

@@ -1,0 +1,211 @@
+"""Chip inference and sliding-window tile inference on B200.
+
+* ``chip_inference`` keeps the signature and loop structure of
+  instageo/model/infer_utils.py:57-136 (batches of ``(data, _), file_names``; argmax -> int8
+  for classification, squeeze for a 1-channel regression head) but the argmax is fused into
+  the last head kernel, so only ``B x 224 x 224`` int8 crosses PCIe instead of float logits.
+* ``sliding_window_inference`` is the path the reference names (``mode=sliding_inference`` in
+  notebooks/InstaGeo_Demo.ipynb, TODO at instageo/model/dataloader.py:693-698) but does not
+  ship; semantics are frozen in SURVEY.md Appendix A.6 / oracle/stitch.py.
+* ``partition`` / ``*_sharded``: chips and windows are independent, so N GPUs (one process
+  each) split the units and only gather int8 results over NCCL (no collective in the model).
+"""
+from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import ops
+from .model import PrithviSeg
+
+
+def save_prediction(prediction: np.ndarray, file_name: str, output_folder: str, profile=None) -> None:
+    """instageo/model/infer_utils.py:37-54; GeoTIFF when rasterio is importable, else ``.npy``."""
+    base = os.path.basename(file_name).replace("chip", "prediction")
+    path = os.path.join(output_folder, base)
+    try:
+        import rasterio  # type: ignore
+    except ImportError:
+        np.save(os.path.splitext(path)[0] + ".npy", prediction)
+        return
+    with rasterio.open(file_name) as src:
+        prof = src.profile
+    prof.update(count=1, dtype=rasterio.int8 if prediction.dtype == np.int8 else rasterio.float32)
+    with rasterio.open(path, "w", **prof) as dst:
+        dst.write(prediction, 1)
+
+
+def chip_inference(dataloader, output_folder: Optional[str], model, device: str = "gpu", num_workers: int = 4,
+                   writer: Optional[Callable] = None) -> dict:
+    """Run inference on chips and hand each prediction to ``writer`` (default ``save_prediction``).
+
+    Returns ``{"predictions": n}`` (the reference returns CodeCarbon info; tracking is out of scope).
+    """
+    device = "cuda" if device == "gpu" else device
+    model.eval()
+    model.to(device)
+    net = getattr(model, "net", model)  # Lightning wrapper keeps the network in .net (base.py:69)
+    writer = writer or (save_prediction if output_folder else None)
+    n = 0
+    with torch.no_grad(), ThreadPoolExecutor(max_workers=num_workers) as pool:
+        for (data, _), file_names in dataloader:
+            data = data.to(device, non_blocking=True)
+            if isinstance(net, PrithviSeg) and net.num_classes > 1:
+                pred = net.predict(data).cpu().numpy()  # fused argmax, int8
+            else:
+                out = model(data)
+                if out.shape[1] == 1:
+                    pred = out.cpu().numpy().squeeze(1)
+                else:
+                    pred = torch.argmax(out, dim=1).cpu().numpy().astype(np.int8)
+            n += len(file_names)
+            if writer is not None:
+                futures = [pool.submit(writer, p, f, output_folder) for p, f in zip(pred, file_names)]
+                for fut in futures:
+                    fut.result()
+    return {"predictions": n}
+
+
+# --------------------------------------------------------------------------- sharding helpers
+def partition(n_units: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced [lo, hi) block of ``n_units`` for ``rank``."""
+    base, rem = divmod(n_units, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def stripe_rows(height: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Output row stripe [y0, y1) owned by ``rank``."""
+    return partition(height, world_size, rank)
+
+
+def windows_for_rows(ys: Sequence[int], win: int, y0: int, y1: int) -> tuple[int, int]:
+    """Range [iy_lo, iy_hi) of window rows intersecting output rows [y0, y1) (halo recompute)."""
+    hit = [i for i, t in enumerate(ys) if t < y1 and t + win > y0]
+    return (hit[0], hit[-1] + 1) if hit else (0, 0)
+
+
+def gather_stripes(local: torch.Tensor, height: int, world_size: int) -> torch.Tensor:
+    """All-gather int8 row stripes into the full [H, W] map (NCCL on GPUs, gloo on CPU)."""
+    import torch.distributed as dist
+
+    if world_size == 1:
+        return local
+    width = local.shape[1]
+    sizes = [partition(height, world_size, r) for r in range(world_size)]
+    rows = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((rows, width), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+
+
+def gather_chip_masks(local: torch.Tensor, n_total: int, world_size: int) -> torch.Tensor:
+    """All-gather per-rank int8 chip masks [n_r, H, W] into dataset order [n_total, H, W]."""
+    import torch.distributed as dist
+
+    if world_size == 1:
+        return local
+    sizes = [partition(n_total, world_size, r) for r in range(world_size)]
+    cap = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+
+
+# --------------------------------------------------------------------------- sliding window
+@torch.no_grad()
+def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224), stride: int = 224,
+                             batch_size: int = 32, device: str = "gpu", *, mean: Sequence[float],
+                             std: Sequence[float], bands: Optional[Sequence[int]] = None,
+                             constant_multiplier: float = 1.0, no_data_value: Optional[float] = None,
+                             nodata_class: int = -1, rows: Optional[tuple[int, int]] = None,
+                             return_tensor: bool = False, fmask=None, fmask_bits: int = 0,
+                             masking_strategy: str = "each"):
+    """Overlap-averaged class map of a raw tile [T*C (or more bands), H, W] (int16 | uint16).
+
+    windows -> fused normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4) -> gather-form
+    overlap average + argmax + nodata (kernel 5).  ``rows=(y0, y1)`` restricts the output to a
+    row stripe and only the windows touching it are computed (multi-GPU halo recompute);
+    per-pixel sums are formed on one rank in fixed order, so any sharding is bit-identical.
+    Returns int8 [y1-y0, W] (numpy unless ``return_tensor``).
+    """
+    device = "cuda" if device == "gpu" else device
+    win = int(window_size[0])
+    if window_size[0] != window_size[1] or win != model.image_size:
+        raise ValueError("window must be square and match the model's image_size")
+    from .dataloader import _to_device
+
+    tile = _to_device(hls_tile, device)
+    if tile.dim() != 3:
+        raise ValueError("hls_tile must be [bands, H, W]")
+    _, H, W = tile.shape
+    if H < win or W < win:
+        raise ValueError(f"tile {H}x{W} is smaller than the window {win}")
+    model.eval()
+    model.to(device)
+    spec = ops.PreprocessSpec(mean, std, model.temporal_step, bands, constant_multiplier, no_data_value, device)
+    ys = ops.window_origins(H, win, stride, edge=True)
+    xs = ops.window_origins(W, win, stride, edge=True)
+    y0, y1 = rows if rows is not None else (0, H)
+    iy_lo, iy_hi = windows_for_rows(ys, win, y0, y1)
+    nx = len(xs)
+    wins = [(0, ys[iy], xs[ix]) for iy in range(iy_lo, iy_hi) for ix in range(nx)]
+    n_win = len(wins)
+    nc = model.num_classes
+    win_t = torch.tensor(wins, dtype=torch.int32, device=device).reshape(-1, 3)
+    logits = torch.empty((n_win, nc, win, win), dtype=torch.float32, device=device)
+    fm = None if fmask is None else _to_device(fmask, device).unsqueeze(0)
+    for s in range(0, n_win, batch_size):
+        e = min(n_win, s + batch_size)
+        pre = ops.preprocess(tile.unsqueeze(0), spec, windows=win_t[s:e], win=win, want_f32=False,
+                             want_patches=True, fmask=fm, fmask_bits=fmask_bits,
+                             masking_strategy=masking_strategy)
+        logits[s:e] = model.forward_patches(pre["patches"], want_logits=True)[0]
+    nodata_px = None
+    if no_data_value is not None or fm is not None:
+        # tile-level "any band is nodata" mask from the same kernel (one whole-tile window per 16-aligned block
+        # is not needed: mask_px of the windows already covers every output pixel; stitch it with OR)
+        nodata_px = _tile_nodata(tile, spec, H, W, win, ys, xs, fm, fmask_bits, masking_strategy)
+    out = ops.stitch(logits, ys, xs, H, W, y0=y0, y1=y1, win_base=iy_lo * nx, nodata_px=nodata_px,
+                     nodata_class=nodata_class)["class_map"]
+    return out if return_tensor else out.cpu().numpy()
+
+
+def _tile_nodata(tile, spec, H, W, win, ys, xs, fm, fmask_bits, masking_strategy) -> torch.Tensor:
+    """[H, W] bool: pixel is nodata in ANY selected band/timestep (after scaling, dataloader.py:899).
+
+    Uses the non-overlapping subset of windows (stride == win plus the edge-aligned ones) so each
+    pixel's mask is computed by kernel 1 and scattered once.
+    """
+    dev = tile.device
+    ty = ops.window_origins(H, win, win, edge=True)
+    tx = ops.window_origins(W, win, win, edge=True)
+    wl = [(0, t, l) for t in ty for l in tx]
+    wt = torch.tensor(wl, dtype=torch.int32, device=dev)
+    m = ops.preprocess(tile.unsqueeze(0), spec, windows=wt, win=win, want_f32=False, want_mask_px=True,
+                       fmask=fm, fmask_bits=fmask_bits, masking_strategy=masking_strategy)["mask_px"]
+    full = torch.zeros((H, W), dtype=torch.bool, device=dev)
+    for i, (_, t, l) in enumerate(wl):
+        full[t:t + win, l:l + win] |= m[i]
+    return full
+
+
+@torch.no_grad()
+def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, world_size: int, **kw):
+    """One process per GPU: each rank computes its output row stripe (halo recompute), then the
+    int8 stripes are all-gathered (the only collective on the path).  Returns the full [H, W] map."""
+    H = hls_tile.shape[1]
+    y0, y1 = stripe_rows(H, world_size, rank)
+    kw = dict(kw)
+    kw["rows"] = (y0, y1)
+    kw["return_tensor"] = True
+    local = sliding_window_inference(hls_tile, model, **kw)
+    return gather_stripes(local, H, world_size)

@@ -1,0 +1,227 @@
+"""GPU bring-up probe: runs one kernel family against a torch reference and prints diagnostics.
+
+    python tools/gpu_probe.py <gemm|ln|attn|pre|stitch|model|all>
+
+Each family is meant to be run in its own process (a device trap poisons the CUDA context).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import instageo_b200  # noqa: E402
+from instageo_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+RES = {}
+
+
+def report(name, got, ref, tol):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    rel = err.max().item() / max(ref.abs().max().item(), 1e-12)
+    bad = (err > tol).float().mean().item()
+    RES[name] = dict(max_abs=err.max().item(), rel=rel, frac_bad=bad, ref_absmax=ref.abs().max().item(),
+                     nan=bool(torch.isnan(got).any()))
+    print(f"[{name}] max_abs={err.max().item():.4e} rel={rel:.3e} frac>{tol}={bad:.4f} nan={RES[name]['nan']}")
+    if bad > 0:
+        idx = (err > tol).nonzero()[:8].tolist()
+        print("   first bad idx:", idx)
+        rows = (err > tol).any(dim=-1).nonzero().flatten()
+        print("   bad rows (first 16):", rows[:16].tolist(), "count", rows.numel(), "of", got.shape[0])
+        cols = (err > tol).any(dim=0).nonzero().flatten() if got.dim() == 2 else []
+        if len(cols):
+            print("   bad cols (first 16):", cols[:16].tolist(), "count", len(cols))
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def probe_gemm():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for (M, N, K) in [(128, 64, 64), (128, 256, 64), (300, 256, 128), (1000, 768, 768), (4096, 2304, 768), (589 * 4, 3072, 768)]:
+        a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+        w = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
+        b = torch.randn(N, generator=g).to(dev)
+        ref = a.float() @ w.float().t() + b
+        out = ops.linear(a, w, b, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        report(f"gemm_f32_{M}x{N}x{K}", out, ref, 2e-3 * max(1.0, ref.abs().max().item()))
+        out = ops.linear(a, w, b, act=1)
+        report(f"gemm_gelu_{M}x{N}x{K}", out, torch.nn.functional.gelu(ref), 2e-2 * max(1.0, ref.abs().max().item()))
+        r = torch.randn(M, N, generator=g).to(dev)
+        r0 = r.clone()
+        out = ops.linear(a, w, b, resid=r)
+        report(f"gemm_resid_{M}x{N}x{K}", out, ref + r0, 2e-3 * max(1.0, ref.abs().max().item()))
+    M, N, K = 37696, 2304, 768
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    b = torch.randn(N, device=dev)
+    ms = timeit(lambda: ops.linear(a, w, b))
+    print(f"[gemm perf] {M}x{N}x{K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s")
+    RES["gemm_tflops_qkv"] = 2 * M * N * K / ms / 1e9
+    ms2 = timeit(lambda: torch.matmul(a, w.t()))
+    print(f"[cublas ref] {ms2:.3f} ms {2*M*N*K/ms2/1e9:.1f} TFLOP/s")
+    RES["cublas_tflops_qkv"] = 2 * M * N * K / ms2 / 1e9
+
+
+def probe_ln():
+    for D in (256, 768, 1024):
+        x = torch.randn(1000, D, device=dev) * 3 + 1
+        g_, b_ = torch.randn(D, device=dev), torch.randn(D, device=dev)
+        ref = torch.nn.functional.layer_norm(x, (D,), g_, b_, 1e-5)
+        report(f"ln_{D}", ops.layernorm(x, g_, b_), ref, 3e-2)
+
+
+def probe_attn():
+    for (B, N, H) in [(1, 128, 1), (2, 197, 4), (2, 589, 12), (3, 64, 2)]:
+        D = H * 64
+        qkv = (torch.randn(B * N, 3 * D, device=dev)).bfloat16()
+        out = ops.attention(qkv, B, N, H)
+        torch.cuda.synchronize()
+        q, k, v = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
+        ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, D)
+        report(f"attn_B{B}_N{N}_H{H}", out, ref, 2e-2)
+    B, N, H = 64, 589, 12
+    qkv = torch.randn(B * N, 3 * H * 64, device=dev).bfloat16()
+    ms = timeit(lambda: ops.attention(qkv, B, N, H))
+    fl = 4 * N * N * 64 * H * B
+    print(f"[attn perf] B{B} N{N} H{H}: {ms:.3f} ms {fl/ms/1e9:.1f} TFLOP/s")
+    RES["attn_tflops"] = fl / ms / 1e9
+
+
+def probe_pre():
+    from oracle import preprocess as OP
+    mean = [0.14245495, 0.13921481, 0.12434631, 0.31420089, 0.20743526, 0.12046503]
+    std = [0.04036231, 0.04186983, 0.05267646, 0.0822221, 0.06834774, 0.05294205]
+    for T, cm, nd in [(1, 1.0, -9999), (3, 1e-4, -9999), (3, 1.0, 0)]:
+        raw = OP.synth_chips(3, T, seed=7, nodata=nd)
+        spec = ops.PreprocessSpec(mean, std, T, constant_multiplier=cm, no_data_value=nd, device=dev)
+        out = ops.preprocess(torch.from_numpy(raw).to(dev), spec, want_f32=True, want_patches=True,
+                             want_mask_elem=True, want_mask_px=True)
+        ref = [OP.preprocess_chip(r, None, cm, mean, std, T, nd) for r in raw]
+        rx = np.stack([r[0] for r in ref]); rm = np.stack([r[1] for r in ref])
+        eq = np.array_equal(out["f32"].cpu().numpy(), rx)
+        meq = np.array_equal(out["mask_elem"].cpu().numpy(), rm)
+        peq = np.array_equal(out["mask_px"].cpu().numpy(), rm.any(axis=1))
+        print(f"[pre T={T} cm={cm} nd={nd}] f32 bit-exact={eq} mask_elem={meq} mask_px={peq} masked={rm.mean():.4f}")
+        RES[f"pre_T{T}_cm{cm}"] = dict(f32=eq, mask_elem=meq, mask_px=peq)
+    n, T = 2048, 3
+    raw = torch.randint(0, 10000, (n, 18, 224, 224), dtype=torch.int16, device=dev)
+    spec = ops.PreprocessSpec(mean, std, T, constant_multiplier=1.0, no_data_value=-9999, device=dev)
+    for tag, kw, bpc in [("parity", dict(want_f32=True, want_mask_elem=True), 18 * 224 * 224 * 7),
+                         ("prod", dict(want_f32=False, want_patches=True, want_mask_px=True), 18 * 224 * 224 * 4 + 224 * 224)]:
+        ms = timeit(lambda: ops.preprocess(raw, spec, **kw), iters=5)
+        print(f"[pre perf {tag}] {n} chips T=3: {ms:.3f} ms  {n*bpc/ms/1e6:.1f} GB/s  {n/ms*1e3:.0f} chips/s")
+        RES[f"pre_gbs_{tag}"] = n * bpc / ms / 1e6
+
+
+def probe_stitch():
+    from oracle import stitch as OS
+    rng = np.random.default_rng(3)
+    for (H, W, win, stride, nc) in [(300, 340, 64, 32, 2), (500, 500, 224, 112, 13), (256, 256, 64, 64, 3)]:
+        ys = ops.window_origins(H, win, stride, True); xs = ops.window_origins(W, win, stride, True)
+        org = [(t, l) for t in ys for l in xs]
+        lg = rng.standard_normal((len(org), nc, win, win)).astype(np.float32)
+        nd = rng.random((H, W)) < 0.05
+        avg, cls = OS.stitch(lg, org, H, W, nd)
+        out = ops.stitch(torch.from_numpy(lg).to(dev), ys, xs, H, W, nodata_px=torch.from_numpy(nd).to(dev),
+                         want_avg=True, want_hist=True)
+        a_eq = np.array_equal(out["avg"].cpu().numpy(), avg)
+        c_eq = np.array_equal(out["class_map"].cpu().numpy(), cls)
+        hist = out["hist"].cpu().numpy()
+        h_ref = [int((cls == k).sum()) for k in range(nc)] + [int((cls == -1).sum())]
+        print(f"[stitch {H}x{W} win{win} s{stride} nc{nc}] avg bit-exact={a_eq} cls={c_eq} hist={list(hist)==h_ref}")
+        RES[f"stitch_{H}_{stride}_{nc}"] = dict(avg=a_eq, cls=c_eq, hist=list(map(int, hist)) == h_ref)
+    H = W = 3660; win = 224; nc = 2
+    for stride in (224, 112):
+        ys = ops.window_origins(H, win, stride, True); xs = ops.window_origins(W, win, stride, True)
+        lg = torch.randn(len(ys) * len(xs), nc, win, win, device=dev)
+        ms = timeit(lambda: ops.stitch(lg, ys, xs, H, W), iters=5)
+        by = lg.numel() * 4 + H * W
+        print(f"[stitch perf stride {stride}] {ms:.3f} ms {by/ms/1e6:.1f} GB/s")
+        RES[f"stitch_gbs_{stride}"] = by / ms / 1e6
+
+
+def probe_model():
+    from instageo_b200.model import PrithviSeg
+    from oracle import prithvi as P
+    for (variant, T, nc, depth, B) in [("prithvi_eo_tiny", 1, 2, 0, 2), ("prithvi_eo_tiny", 1, 2, 1, 2),
+                                       ("prithvi_eo_tiny", 3, 13, 2, 2), ("prithvi_eo_v1_100", 1, 2, 2, 2)]:
+        tag = f"{variant}_T{T}_nc{nc}_d{depth}"
+        sd = P.make_state_dict(variant, T, nc, depth=depth, seed=5, stress=True)
+        m = PrithviSeg(temporal_step=T, num_classes=nc, load_pretrained_weights=False, variant=variant, depth=depth)
+        m.load_state_dict(sd, strict=True)
+        m.to(dev).eval()
+        x = torch.randn(B, 6, T, 224, 224, generator=torch.Generator().manual_seed(1))
+        taps = {}
+        ref = P.prithvi_seg_forward(x, sd, P.VARIANTS[variant][2], T, taps=taps)
+        try:
+            out, feat = m(x.to(dev), return_features=True)
+            torch.cuda.synchronize()
+        except Exception as e:
+            print(f"[{tag}] FAILED: {e}")
+            RES[tag] = str(e)
+            raise
+        D = P.VARIANTS[variant][0]
+        N = 1 + T * 196
+        xres = m.debug_tap("x", B, (B, N, D))
+        report(f"{tag}_x", xres, taps[f"block{depth-1}"] if depth > 0 else taps["embed"], 5e-2)
+        report(f"{tag}_feat", feat, P.tokens_to_image(taps["tokens"], T), 5e-2)
+        dims = P.head_dims(D, T)
+        hw = 14
+        for i in range(4):
+            hw *= 2
+            report(f"{tag}_convt{i}", m.debug_tap(f"convt{i}", B, (B, dims[i + 1], hw, hw)), taps[f"convt{i}"], 5e-2)
+            if i < 3:
+                report(f"{tag}_stage{i}", m.debug_tap(f"stage{i}", B, (B, dims[i + 1], hw, hw)), taps[f"stage{i}"], 5e-2)
+        report(f"{tag}_logits", out, ref, 2e-2)
+        am = m.predict(x.to(dev)).cpu()
+        top2 = ref.topk(2, dim=1).values
+        eps = (out.cpu() - ref).abs().max().item()
+        safe = (top2[:, 0] - top2[:, 1]) > 2 * eps
+        agree = (am.long() == ref.argmax(1))[safe].float().mean().item()
+        print(f"[{tag}] argmax agree outside ties {agree:.5f} (safe frac {safe.float().mean().item():.3f})")
+        RES[f"{tag}_argmax"] = dict(agree=agree, safe=safe.float().mean().item())
+        del m
+
+
+def probe_bench():
+    from instageo_b200.model import PrithviSeg
+    for (variant, T, nc, B) in [("prithvi_eo_v1_100", 3, 13, 64)]:
+        m = PrithviSeg(temporal_step=T, num_classes=nc, load_pretrained_weights=False, variant=variant).to(dev).eval()
+        x = torch.randn(B, 6, T, 224, 224, device=dev)
+        ms = timeit(lambda: m.predict(x), iters=5)
+        print(f"[bench {variant} T{T} B{B}] {ms:.2f} ms/step {B/ms*1e3:.1f} chips/s")
+        RES[f"bench_{variant}_T{T}_B{B}"] = B / ms * 1e3
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    fams = dict(gemm=probe_gemm, ln=probe_ln, attn=probe_attn, pre=probe_pre, stitch=probe_stitch,
+                model=probe_model, bench=probe_bench)
+    t0 = time.time()
+    try:
+        for k, f in fams.items():
+            if which in (k, "all"):
+                f()
+    finally:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"probe_{which}.json"), "w") as fh:
+            json.dump(RES, fh, indent=1, default=str)
+        print(f"probe {which} done in {time.time()-t0:.1f}s")
