@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads and exports every symbol include/instageo_b200.h declares;
+the host mirror refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+import instageo_b200
+from instageo_b200 import _lib
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "instageo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ig_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype in _lib.py"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.ig_version() >= 100
+    assert isinstance(lib.ig_last_error(), bytes)
+
+
+def test_no_cpu_fallback():
+    from instageo_b200.model import PrithviSeg
+    m = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_tiny", depth=1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 6, 1, 224, 224))
+    from instageo_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.stitch(torch.zeros(1, 2, 8, 8), [0], [0], 8, 8)
+    m.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(torch.zeros(1, 6, 1, 224, 224))
+
+
+def test_state_dict_is_drop_in():
+    """Same keys/shapes as the reference PrithviSeg (188 tensors for V1-100M; model.py:292-390)."""
+    from instageo_b200.model import PrithviSeg
+    from oracle import prithvi as P
+    m = PrithviSeg(temporal_step=3, num_classes=13, load_pretrained_weights=False, variant="prithvi_eo_v1_100", depth=2)
+    sd = m.state_dict()
+    ref = P.make_state_dict("prithvi_eo_v1_100", 3, 13, depth=2)
+    assert set(sd) == set(ref)
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in sd)
+    m.load_state_dict(ref, strict=True)
+    full = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_tiny")
+    assert len(full.state_dict()) == 4 + 12 * 4 + 2 + 38
+    assert not any(p.requires_grad for p in full.prithvi_encoder.parameters())  # freeze_backbone default
+    assert torch.equal(m.prithvi_encoder.pos_embed, ref["prithvi_encoder.pos_embed"])
+    tl = PrithviSeg(temporal_step=1, load_pretrained_weights=False, variant="prithvi_eo_v2_300_tl", depth=0)
+    assert "prithvi_encoder.temporal_embed_enc.scale" in tl.state_dict()
+    with pytest.raises(NotImplementedError):
+        PrithviSeg(load_pretrained_weights=False, variant="prithvi_eo_v2_600")
