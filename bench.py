@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""Headline benchmark: 224-px 6-band chips/sec through the chip-inference hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): Prithvi-V1-100M PrithviSeg, multi-temporal crop
+segmentation shape (6 bands x 3 timesteps x 224 x 224, 13 classes), batch 64 per GPU, random-init
+weights, synthetic int16 chips.  One step = raw int16 chips -> fused normalise/mask (kernel 1) ->
+PrithviSeg (kernels 2-4) -> argmax int8 (fused).  N > 1: one process per GPU (torchrun), every rank
+its own 64 chips (weak scaling), one NCCL all-gather of the int8 masks per step -- no other collective.
+
+`--impl reference` times the reference's own CPU algorithm (the in-repo oracle port: the reference
+is pure Python/PyTorch and is not present on the GPU box) on the host cores, same config and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VARIANT, T, NC, BATCH = "prithvi_eo_v1_100", 3, 13, 64
+CROP_MEAN = [494.905781, 815.239594, 924.335066, 2968.881459, 2634.621962, 1739.579917]
+CROP_STD = [284.925432, 357.84876, 575.566823, 896.601013, 951.900334, 921.407808]
+METRIC = "224px 6-band chips/sec/box (device-timed)"
+WORKLOAD = "prithvi_v1_100m_T3_nc13_b64: raw int16 chips -> normalise/mask -> PrithviSeg -> argmax int8"
+CPU_SAMPLE_CHIPS = 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1436.2), d.get("hbm_gbs", 6456.2), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_step(sd, raw, heads):
+    """Reference CPU path for a chip batch: normalise/mask -> PrithviSeg fp32 -> argmax int8."""
+    import numpy as np
+    import torch
+    from oracle import preprocess as OP
+    from oracle import prithvi as P
+    x = np.stack([OP.preprocess_chip(r, None, 1.0, CROP_MEAN, CROP_STD, T, None)[0] for r in raw])
+    return P.argmax_int8(P.prithvi_seg_forward(torch.from_numpy(x), sd, heads, T))
+
+
+def cpu_setup():
+    import torch
+    from oracle import preprocess as OP
+    from oracle import prithvi as P
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    sd = P.make_state_dict(VARIANT, T, NC, seed=0, stress=True)
+    raw = OP.synth_chips(CPU_SAMPLE_CHIPS, T, seed=1042, nodata=None)
+    return sd, raw, P.VARIANTS[VARIANT][2], torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sd, raw, heads, cores = cpu_setup()
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_oracle_step(sd, raw, heads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_step(sd, raw, heads)
+    dt = time.perf_counter() - t0
+    v = CPU_SAMPLE_CHIPS * args.steps / dt
+    sample = f"{CPU_SAMPLE_CHIPS} chips/step of the same workload (of {BATCH}), oracle port of the reference CPU path, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "chips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "chips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import instageo_b200
+    from instageo_b200 import _lib, ops
+    from instageo_b200.model import PrithviSeg
+    from instageo_b200.model.infer_utils import ChipPipeline
+    from instageo_b200.model.model import flops_per_chip
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    torch.manual_seed(0)
+    model = PrithviSeg(temporal_step=T, num_classes=NC, load_pretrained_weights=False, variant=VARIANT).to(dev).eval()
+    spec = ops.PreprocessSpec(CROP_MEAN, CROP_STD, T, None, 1.0, None, dev)
+    g = torch.Generator(device="cpu").manual_seed(1042 + rank)
+    n_rot = 4  # rotating input batches: 4 x 115.6 MB > 126 MB L2
+    raws = [torch.randint(0, 10001, (BATCH, T * 6, 224, 224), generator=g, dtype=torch.int16) for _ in range(n_rot)]
+    d_raws = [r.to(dev) for r in raws]
+    gathered = [torch.empty((BATCH, 224, 224), dtype=torch.int8, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step(i):
+        pre = ops.preprocess(d_raws[i % n_rot], spec, want_f32=False, want_patches=True)
+        amax = model.forward_patches(pre["patches"], want_logits=False, want_argmax=True)[1]
+        if world > 1:
+            dist.all_gather(gathered, amax)
+        return amax
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    launches_per_step = 1 + model.launches_per_forward() - 1  # preprocess + forward (no patchify: bf16 rows in)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM: encoder linears + head implicit-GEMM convs):
+    # CUDA events around every launch on its own stream, over `steps` instrumented steps of the same loop.
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize()
+    fam = _lib.profile_report()
+    _lib.profile_enable(False)
+    enc = model.prithvi_encoder
+    fl = flops_per_chip(enc.embed_dim, len(enc.blocks), T, NC)
+    n_tok = T * 196 + 1
+    attn_fl = len(enc.blocks) * 4 * n_tok * n_tok * enc.embed_dim
+    gemm_fl_step = (fl["total"] - attn_fl) * BATCH
+    gemm_ms = fam["gemm_linear"][0] + fam["gemm_conv"][0]
+    gemm_launches = fam["gemm_linear"][1] + fam["gemm_conv"][1]
+    peak_tf, peak_gbs, peak_src = peaks()
+    achieved = gemm_fl_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    all_ms = sum(v[0] for v in fam.values())
+    roofline = {"kernel": "gemm_kernel<EPI> (tcgen05 GEMM: encoder linears + head implicit-GEMM convs)",
+                "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "algorithmic_flops_per_launch": gemm_fl_step * args.steps / max(1, gemm_launches),
+                "avg_launch_ms": gemm_ms / max(1, gemm_launches), "share_of_step": gemm_ms / all_ms if all_ms else None,
+                "timing": "cuda events around every launch, %d instrumented steps right after the timed region" % args.steps}
+    families = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in fam.items()}
+    pre_bytes = BATCH * (T * 6 * 224 * 224 * 4)  # int16 in + bf16 out
+    if fam["preprocess"][0] > 0:
+        families["preprocess"]["achieved_gbs"] = pre_bytes * args.steps / (fam["preprocess"][0] / 1e3) / 1e9
+        families["preprocess"]["frac_of_hbm_peak"] = families["preprocess"]["achieved_gbs"] / peak_gbs
+
+    # ---- end to end through the public host API (host buffers, H2D + D2H inside the timed region)
+    pipe = ChipPipeline(model, spec, BATCH, dev)
+    pinned = [r.pin_memory() for r in raws]
+    sink = []
+    pipe.run([pinned[i % n_rot] for i in range(args.warmup)], consume=lambda a: None)
+    barrier()
+    t0 = time.perf_counter()
+    pipe.run([pinned[i % n_rot] for i in range(args.steps)], consume=lambda a: sink.append(int(a[0, 0, 0])))
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * BATCH * args.steps / dt.item(), "unit": "chips/s",
+           "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "api": "instageo_b200.model.infer_utils.ChipPipeline.run (pinned host int16 in, int8 masks out)"}
+
+    out = {"metric": METRIC, "value": value, "unit": "chips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                      "parallelism": f"chip-sharded x{world}, int8 mask all-gather" if world > 1 else "single GPU",
+                      "l2": "4 rotating input batches (462 MB int16) + >1 GB of activations per step, larger than the 126 MB L2"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
+           "kernel_families": families}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd, raw, heads, cores = cpu_setup()
+        cpu_oracle_step(sd, raw[:1], heads)
+        t0, n = time.perf_counter(), 0
+        while n < 3 and (n == 0 or time.perf_counter() - t0 < 12):
+            cpu_oracle_step(sd, raw, heads)
+            n += 1
+        v = CPU_SAMPLE_CHIPS * n / (time.perf_counter() - t0)
+        out["cpu_baseline"] = {"value": v, "unit": "chips/s", "cores": cores, "kind": "port",
+                               "sample": f"{n} x {CPU_SAMPLE_CHIPS} chips of the same workload through oracle/ (reference CPU path, fp32)"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

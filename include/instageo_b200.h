@@ -160,6 +160,14 @@ int ig_layernorm(const float* x, const float* gamma, const float* beta, void* ou
 /* qkv bf16 [B*N, 3*D] (timm layout: q | k | v, head-major inside) -> out bf16 [B*N, D] */
 int ig_attention(const void* qkv, void* out, int B, int N, int heads, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Measurement aid (bench.py roofline): when enabled, every launch is bracketed by CUDA events on
+ * its own stream.  Families: 0 preprocess, 1 stitch, 2 encoder GEMMs, 3 head implicit-GEMM convs,
+ * 4 attention, 5 layernorm, 6 other.  ig_profile_report sums and clears (blocks on the events). */
+#define IG_PROF_FAMILIES 7
+int ig_profile_enable(int on);
+int ig_profile_report(double* ms, int* launches, int ncat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ SIGNATURES = {
     "ig_linear": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ig_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ig_attention": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ig_profile_enable": (_I, [_I]),
+    "ig_profile_report": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int), _I]),
 }
 
 _lib = None
@@ -85,3 +87,18 @@ def current_stream() -> int:
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+PROF_FAMILIES = ["preprocess", "stitch", "gemm_linear", "gemm_conv", "attention", "layernorm", "other"]
+
+
+def profile_enable(on: bool) -> None:
+    check(load().ig_profile_enable(int(on)))
+
+
+def profile_report() -> dict:
+    """{family: (milliseconds, launches)} since the last report."""
+    n = len(PROF_FAMILIES)
+    ms, cnt = (C.c_double * n)(), (C.c_int * n)()
+    check(load().ig_profile_report(ms, cnt, n))
+    return {f: (ms[i], cnt[i]) for i, f in enumerate(PROF_FAMILIES)}

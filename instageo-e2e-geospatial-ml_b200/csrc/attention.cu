@@ -252,6 +252,7 @@ int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t 
   CUtensorMap tm;
   IG_TRY(ig_make_tmap_bf16(&tm, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, 128, 64));
   dim3 grid((N + attn::BQ - 1) / attn::BQ, heads, B);
+  ig::ProfScope prof(ig::PROF_ATTENTION, st);
   attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_TOTAL, st>>>(tm, static_cast<__nv_bfloat16*>(out), N, D);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;

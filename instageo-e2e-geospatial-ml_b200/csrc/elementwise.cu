@@ -83,6 +83,7 @@ int layernorm(const float* x, const float* gamma, const float* beta, void* out, 
   if (M <= 0) return IG_OK;
   LnArgs a{x, gamma, beta, static_cast<__nv_bfloat16*>(out), M, D, mode, ntok, T, g, guard};
   const int wpb = 8;
+  ig::ProfScope prof(ig::PROF_LAYERNORM, st);
   layernorm_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
@@ -123,6 +124,7 @@ int patchify(const float* x, void* out, int B, int C, int T, int S, cudaStream_t
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(ig_num_sms()) * 32;
   if (blocks > cap) blocks = cap;
+  ig::ProfScope prof(ig::PROF_MISC, st);
   patchify_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), B, C, T, S);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
@@ -136,6 +138,7 @@ __global__ void cls_kernel(float* x, const float* cls, const float* pos, int B, 
   x[static_cast<int64_t>(b) * ntok * D + d] = cls[d] + pos[d];
 }
 int init_cls(float* x, const float* cls, const float* pos, int B, int ntok, int D, cudaStream_t st) {
+  ig::ProfScope prof(ig::PROF_MISC, st);
   cls_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(x, cls, pos, B, ntok, D);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
@@ -166,6 +169,7 @@ int zero_ring(void* buf, int B, int Hp, int Wp, int C, cudaStream_t st) {
   if (total <= 0) return IG_OK;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  ig::ProfScope prof(ig::PROF_MISC, st);
   ring_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<__nv_bfloat16*>(buf), B, Hp, Wp, C);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
@@ -259,6 +263,7 @@ __global__ void unpad_kernel(const __nv_bfloat16* buf, float* dst, int B, int Hp
   }
 }
 int unpad_to_nchw(const void* buf, float* dst, int B, int Hp, int Wp, int C, int guard, int permT, cudaStream_t st) {
+  ig::ProfScope prof(ig::PROF_MISC, st);
   unpad_kernel<<<2048, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(buf), dst, B, Hp, Wp, C, guard, permT);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;

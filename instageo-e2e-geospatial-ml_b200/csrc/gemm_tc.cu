@@ -364,6 +364,7 @@ static int launch_epi(const Plan& p, cudaStream_t stream) {
   const int total = p.args.num_m_tiles * p.args.num_n_tiles * p.args.num_phases;
   if (total <= 0) return IG_OK;
   const int grid = total < ig_num_sms() ? total : ig_num_sms();
+  ig::ProfScope prof((EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) ? ig::PROF_GEMM_CONV : ig::PROF_GEMM_LINEAR, stream);
   gemm_kernel<EPI><<<grid, THREADS, SMEM_TOTAL, stream>>>(p.tmA, p.tmB, p.args);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;

@@ -43,6 +43,21 @@ int ig_num_sms();
 int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_pitch, uint32_t box_rows, uint32_t box_cols);
 
+// Optional per-launch CUDA-event timing (ig_profile_enable): brackets a launch with two events on
+// the launching stream; ig_profile_report sums elapsed time per kernel family.
+namespace ig {
+enum ProfCat { PROF_PREPROCESS = 0, PROF_STITCH, PROF_GEMM_LINEAR, PROF_GEMM_CONV, PROF_ATTENTION,
+               PROF_LAYERNORM, PROF_MISC, PROF_COUNT };
+void prof_begin(int cat, cudaStream_t st);
+void prof_end(int cat, cudaStream_t st);
+struct ProfScope {
+  int cat;
+  cudaStream_t st;
+  ProfScope(int c, cudaStream_t s) : cat(c), st(s) { prof_begin(cat, st); }
+  ~ProfScope() { prof_end(cat, st); }
+};
+}  // namespace ig
+
 // ----------------------------------------------------------------------------- device PTX
 #ifdef __CUDACC__
 namespace ig {

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "ig_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -81,5 +84,58 @@ int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IG_REQUIRE(r == CUDA_SUCCESS, IG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)",
              static_cast<int>(r), static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols));
+  return IG_OK;
+}
+
+// ----------------------------------------------------------------------------- launch profiling
+namespace {
+struct ProfRec { int cat; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_open[ig::PROF_COUNT];
+}  // namespace
+
+void ig::prof_begin(int cat, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_open[cat].push_back(e);
+}
+void ig::prof_end(int cat, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_open[cat].empty()) return;
+  cudaEvent_t e0 = g_open[cat].back();
+  g_open[cat].pop_back();
+  cudaEvent_t e1;
+  if (cudaEventCreate(&e1) != cudaSuccess) return;
+  cudaEventRecord(e1, st);
+  g_prof.push_back({cat, e0, e1});
+}
+
+extern "C" int ig_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return IG_OK;
+}
+
+// ms[c] = summed device time of family c since the last report, launches[c] = launch count.
+extern "C" int ig_profile_report(double* ms, int* launches, int ncat) {
+  IG_REQUIRE(ms && launches && ncat >= ig::PROF_COUNT, IG_EINVAL, "ig_profile_report: need %d categories", ig::PROF_COUNT);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      ms[r.cat] += t;
+      launches[r.cat] += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
   return IG_OK;
 }

@@ -257,6 +257,7 @@ extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_sr
   const int64_t cap = static_cast<int64_t>(ig_num_sms()) * 8 * 4;  // 8 resident CTAs/SM, 4 waves
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ig::ProfScope prof(ig::PROF_PREPROCESS, st);
   if (raw_dtype == IG_I16)
     preprocess_kernel<int16_t><<<static_cast<unsigned>(blocks), threads, 0, st>>>(a);
   else if (raw_dtype == IG_U16)

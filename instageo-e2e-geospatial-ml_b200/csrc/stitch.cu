@@ -32,6 +32,7 @@ struct StitchArgs {
   unsigned long long* hist;
 };
 
+template <int NCM>
 __global__ void __launch_bounds__(256) stitch_kernel(const StitchArgs a) {
   __shared__ int s_xs[MAX_AX];
   __shared__ int s_iy0, s_iy1;
@@ -40,16 +41,16 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchArgs a) {
   for (int i = threadIdx.x; i < a.nx; i += blockDim.x) s_xs[i] = a.xs[i];
   if (threadIdx.x <= a.nc && threadIdx.x <= MAX_NC) s_hist[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    int lo = a.ny, hi = 0;
-    for (int i = 0; i < a.ny; ++i) {
-      const int o = a.ys[i];
-      if (o <= y && y < o + a.win) {
-        lo = min(lo, i);
-        hi = max(hi, i + 1);
-      }
+    s_iy0 = a.ny;
+    s_iy1 = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.ny; i += blockDim.x) {  // parallel cover test, no serial global loads
+    const int o = a.ys[i];
+    if (o <= y && y < o + a.win) {
+      atomicMin(&s_iy0, i);
+      atomicMax(&s_iy1, i + 1);
     }
-    s_iy0 = lo;
-    s_iy1 = hi;
   }
   __syncthreads();
   const int iy0 = s_iy0, iy1 = s_iy1;
@@ -60,9 +61,9 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchArgs a) {
     const int x = xb + threadIdx.x;
     int cls = a.nodata_class;
     if (x < a.W) {
-      float acc[MAX_NC];
+      float acc[NCM];
 #pragma unroll
-      for (int k = 0; k < MAX_NC; ++k) acc[k] = 0.f;
+      for (int k = 0; k < NCM; ++k) acc[k] = 0.f;
       float cnt = 0.f;
       for (int iy = iy0; iy < iy1; ++iy) {
         const int ly = y - a.ys[iy];
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchArgs a) {
           if (wi < 0 || wi >= a.n_win) continue;
           const float* p = a.logits + static_cast<int64_t>(wi) * a.nc * plane + ly * a.win + lx;
 #pragma unroll
-          for (int k = 0; k < MAX_NC; ++k)
+          for (int k = 0; k < NCM; ++k)
             if (k < a.nc) acc[k] = __fadd_rn(acc[k], __ldcs(p + k * plane));
           cnt += 1.f;
         }
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchArgs a) {
       float best = 0.f;
       int bi = 0;
 #pragma unroll
-      for (int k = 0; k < MAX_NC; ++k)
+      for (int k = 0; k < NCM; ++k)
         if (k < a.nc) {
           const float v = covered ? __fdiv_rn(acc[k], cnt) : 0.f;
           if (a.avg) a.avg[(static_cast<int64_t>(k) * rows + (y - a.y0)) * a.W + x] = v;
@@ -131,7 +132,12 @@ extern "C" int ig_stitch(const float* win_logits, int n_win, int win_base, int n
                nodata_px, nodata_class, avg, class_map, hist};
   const int threads = 256;
   dim3 grid((W + threads - 1) / threads, y1 - y0);
-  stitch_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ig::ProfScope prof(ig::PROF_STITCH, st);
+  if (nc <= 2) stitch_kernel<2><<<grid, threads, 0, st>>>(a);
+  else if (nc <= 4) stitch_kernel<4><<<grid, threads, 0, st>>>(a);
+  else if (nc <= 16) stitch_kernel<16><<<grid, threads, 0, st>>>(a);
+  else stitch_kernel<MAX_NC><<<grid, threads, 0, st>>>(a);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }

@@ -209,3 +209,86 @@ def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, wor
     kw["return_tensor"] = True
     local = sliding_window_inference(hls_tile, model, **kw)
     return gather_stripes(local, H, world_size)
+
+
+# --------------------------------------------------------------------------- host <-> device pipeline
+class ChipPipeline:
+    """The call a user makes for a stream of raw chip batches held in HOST memory.
+
+    ``run(batches)``: for every [B, T*C, 224, 224] int16/uint16 host array -> int8 class masks
+    [B, 224, 224] on the host.  Per step: pinned H2D copy of the raw integers (2 B/element, not
+    the 4 B/element float tensor the reference ships, instageo/model/infer_utils.py:93), fused
+    normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4, argmax fused) -> D2H of the int8 masks
+    (1 B/pixel instead of float logits, :99-101).  Copies run on a side stream and overlap the
+    previous step's compute (double buffering); results are identical to the unpipelined path.
+    """
+
+    def __init__(self, model: PrithviSeg, spec: ops.PreprocessSpec, batch: int, device="cuda",
+                 raw_dtype=torch.int16):
+        self.model, self.spec, self.batch = model, spec, batch
+        self.device = torch.device(device)
+        S, tc = model.image_size, spec.T * spec.C
+        n_src = max(spec.bands) + 1
+        self.h_in = [torch.empty((batch, n_src, S, S), dtype=torch.int16).pin_memory() for _ in range(2)]
+        self.d_in = [torch.empty((batch, n_src, S, S), dtype=torch.int16, device=self.device) for _ in range(2)]
+        self.h_out = [torch.empty((batch, S, S), dtype=torch.int8).pin_memory() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.in_ready = [torch.cuda.Event() for _ in range(2)]
+        self.in_free = [torch.cuda.Event() for _ in range(2)]
+        self.out_ready = [torch.cuda.Event() for _ in range(2)]
+        self.raw_dtype = raw_dtype
+        self.h2d_bytes = batch * n_src * S * S * 2
+        self.d2h_bytes = batch * S * S
+        model.eval()
+
+    def _upload(self, slot: int, host_batch) -> None:
+        src = host_batch if isinstance(host_batch, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host_batch))
+        if src.dtype == torch.uint16:
+            src = src.view(torch.int16)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.in_free[slot])
+            if src.is_pinned():
+                self.d_in[slot].copy_(src, non_blocking=True)
+            else:
+                self.h_in[slot].copy_(src)
+                self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
+            self.in_ready[slot].record(self.copy_stream)
+
+    def _compute(self, slot: int) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.in_ready[slot])
+        raw = self.d_in[slot] if self.raw_dtype == torch.int16 else self.d_in[slot].view(torch.uint16)
+        pre = ops.preprocess(raw, self.spec, win=self.model.image_size, want_f32=False, want_patches=True)
+        amax = self.model.forward_patches(pre["patches"], want_logits=False, want_argmax=True)[1]
+        self.in_free[slot].record(cur)
+        self.h_out[slot].copy_(amax, non_blocking=True)
+        self.out_ready[slot].record(cur)
+
+    @torch.no_grad()
+    def run(self, batches, consume: Optional[Callable] = None) -> int:
+        """Process an iterable of host batches; ``consume(np.ndarray int8 [B,224,224])`` per batch."""
+        n, pending = 0, None
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is not None:
+            self._upload(0, nxt)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            cur_batch = nxt
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload(slot ^ 1, nxt)   # overlaps with the compute below
+            self._compute(slot)
+            if pending is not None:
+                self.out_ready[pending].synchronize()
+                if consume is not None:
+                    consume(self.h_out[pending].numpy())
+            pending = slot
+            n += len(cur_batch)
+            i += 1
+        if pending is not None:
+            self.out_ready[pending].synchronize()
+            if consume is not None:
+                consume(self.h_out[pending].numpy())
+        return n
