@@ -1,15 +1,24 @@
-// Kernels 2-4 core: persistent, warp-specialised tcgen05 GEMM with TMEM accumulators.
+// Kernels 2-4 core: persistent, warp-specialised tcgen05 GEMM on CTA PAIRS (cta_group::2).
 //
-//   D[128 x block_n] (f32, TMEM) += A[128 x 64] (bf16, smem via TMA) * B[block_n x 64]^T
+//   D[256 x block_n] (f32, 128 TMEM lanes in each CTA of the pair)
+//       += A[256 x 64] (bf16, 128 rows in each CTA's smem) * B[block_n x 64]^T (half in each CTA)
 //
-// Roles (320 threads, 1 CTA per SM):
-//   warp 0      TMA producer   : 4-stage ring of {A 16 KB, B <= 32 KB} tiles, 128-byte swizzle
-//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (UMMA 128 x block_n x 16),
-//                                commits free the smem stage / publish the accumulator
-//   warps 2-9   epilogue       : tcgen05.ld the accumulator (2 warps per TMEM lane quadrant,
-//                                interleaved 16-column chunks), fused epilogue, global stores
-// Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the
-// main loop of tile i+1.
+// Why pairs: a 128 x 256 single-CTA tile needs 48 KB of operands per 64-wide K step, i.e. ~96 B/clk/SM
+// or >14 KB/clk chip-wide from L2 -- more than the L2 delivers, and the measured 1-CTA kernel sat at
+// ~45 % of cuBLAS for exactly that reason.  With cta_group::2 each CTA loads its own 128 A rows and only
+// HALF of the B tile (the UMMA reads both CTAs' shared memories), 32 KB per step for the same math.
+//
+// Roles per CTA (320 threads, 1 CTA per SM, cluster = 2 CTAs = one TPC):
+//   warp 0      TMA producer   : 5-stage ring of {A 16 KB, B-half <= 16 KB}, 128-byte swizzle; both CTAs'
+//                                loads complete on the LEADER's full barrier
+//   warp 1      MMA issuer     : leader CTA only; one lane issues tcgen05.mma.cta_group::2 (UMMA
+//                                256 x block_n x 16); commits are multicast to both CTAs' barriers
+//   warps 2-9   epilogue       : tcgen05.ld the CTA's 128 accumulator rows (2 warps per TMEM lane
+//                                quadrant), fused epilogue in registers (thread = row), then a swizzled
+//                                per-warp smem transpose so that every global access of the epilogue
+//                                (bf16/f32 store, f32 residual read, pos-embed read) is a full 128-byte
+//                                line per row instead of 32 scattered 16-byte pieces
+// Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // The same kernel runs the segmentation head as an implicit GEMM with NO im2col: activations
 // live in a zero-bordered "padded-flat" NHWC layout [B*(H+2)*(W+2), C], so a 3x3 tap (dy,dx)
@@ -25,21 +34,25 @@
 
 namespace gemm {
 
-constexpr int A_BYTES = BM * BK * 2;          // 16384
-constexpr int B_BYTES = MAX_BN * BK * 2;      // 32768 (reserved; block_n*128 used)
+constexpr int A_BYTES = BM * BK * 2;              // 16384: this CTA's 128 rows
+constexpr int B_BYTES = (MAX_BN / 2) * BK * 2;    // 16384 reserved: this CTA's half of the B tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;               // 196608
-constexpr int SMEM_BARS = 128;                                // barriers + tmem ptr
-constexpr int SMEM_FINAL = MAX_BN * NCP * 4 + 2 * BM * NCP * 4;  // w1 + exchange
-constexpr int SMEM_TOTAL = 1024 + SMEM_MAIN + SMEM_BARS + SMEM_FINAL;
+constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;   // 163840
+constexpr int STG_BYTES = 32 * 128;               // per-warp transpose tile: 32 rows x 128 B
+constexpr int SMEM_STAGING = NUM_EPI_WARPS * STG_BYTES;  // 32768 (EPI_FINAL: cross-half logit exchange)
+constexpr int SMEM_W1 = MAX_BN * NCP * 4;         // 16384 (EPI_FINAL 1x1 weights)
+constexpr int SMEM_BARS = 256;                    // barriers + tmem ptr
+constexpr int SMEM_TOTAL = 1024 + SMEM_MAIN + SMEM_STAGING + SMEM_W1 + SMEM_BARS;
+static_assert(2 * BM * NCP * 4 <= SMEM_STAGING, "logit exchange must fit the staging area");
+static_assert(SMEM_TOTAL <= 232448, "over the 227 KB shared-memory limit");
 
 struct RowInfo {
   bool valid;      // row < M
   bool interior;   // conv modes: not a border pixel
-  int img, yy, xx; // conv modes: padded coordinates
+  int img, yy, xx; // conv modes: padded coordinates (EPI_PATCH: xx = token index)
   int64_t orow;    // output row (mode dependent)
 };
 
@@ -73,70 +86,82 @@ __device__ __forceinline__ RowInfo make_row(const Args& a, int r, int phase) {
   return ri;
 }
 
+// 16-byte chunk `chunk` of staging row `row`, XOR-swizzled so that both the row-per-thread writes and
+// the 4-rows-per-instruction read-back are bank-conflict free.
+__device__ __forceinline__ uint4* stg_slot(uint8_t* stg, int row, int chunk) {
+  return reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SMEM_MAIN);
+  uint8_t* stg_base = smem + SMEM_MAIN;
+  float* w1s = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_STAGING);  // [N][NCP]
+  float* exch = reinterpret_cast<float*>(stg_base);                         // [2][BM][NCP] (EPI_FINAL)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SMEM_MAIN + SMEM_STAGING + SMEM_W1);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* w1s = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_BARS);  // [N][NCP]
-  float* exch = w1s + MAX_BN * NCP;                                      // [2][BM][NCP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ig::cluster_ctarank();       // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int tiles_per_phase = a.num_m_tiles * a.num_n_tiles;
   const int total_tiles = tiles_per_phase * a.num_phases;
   const int kblocks_per_tap = (a.kc + BK - 1) / BK;
+  const int half_n = a.block_n >> 1;
 
   if (warp == 0 && lane == 0) {
     ig::tma_prefetch_desc(&tmA);
     ig::tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      ig::mbar_init(&full[s], 1);
-      ig::mbar_init(&empty[s], 1);
+      ig::mbar_init(&full[s], 1);    // leader: its own expect_tx arrive; bytes from both CTAs
+      ig::mbar_init(&empty[s], 1);   // one multicast commit per use
     }
     for (int s = 0; s < 2; ++s) {
       ig::mbar_init(&tfull[s], 1);
-      ig::mbar_init(&tempty[s], NUM_EPI_WARPS);
+      ig::mbar_init(&tempty[s], 2 * NUM_EPI_WARPS);  // leader: epilogue warps of both CTAs
     }
     ig::fence_barrier_init();
   }
   if (warp == 1) {
-    ig::tmem_alloc(tmem_ptr, TMEM_COLS);
-    ig::tmem_relinquish();
+    ig::tmem_alloc_cg2(tmem_ptr, TMEM_COLS);
+    ig::tmem_relinquish_cg2();
   }
   if (EPI == EPI_FINAL) {
     for (int i = threadIdx.x; i < a.N * NCP; i += THREADS) w1s[i] = a.w1[i];
   }
   ig::tc_fence_before();
   __syncthreads();
+  ig::cluster_sync();  // peer barriers are initialised before anyone signals them
   ig::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t ph = 0;
-      const uint32_t tx_bytes = A_BYTES + a.block_n * BK * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t tx_bytes = 2u * (A_BYTES + half_n * BK * 2);  // both CTAs' boxes
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
         const int phase = tile / tiles_per_phase;
         const int rem = tile - phase * tiles_per_phase;
-        const int m0 = (rem / a.num_n_tiles) * BM;
-        const int n0 = (rem % a.num_n_tiles) * a.block_n;
+        const int m0 = (rem / a.num_n_tiles) * PAIR_M + static_cast<int>(rank) * BM;
+        const int nb0 = (rem % a.num_n_tiles) * a.block_n + static_cast<int>(rank) * half_n;
         const Taps& tp = a.taps[phase];
         for (int t = 0; t < tp.n; ++t) {
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
             ig::mbar_wait(&empty[stage], ph ^ 1);
-            ig::mbar_expect_tx(&full[stage], tx_bytes);
+            if (rank == 0) ig::mbar_expect_tx(&full[stage], tx_bytes);
+            const uint32_t bar = ig::mapa_u32(&full[stage], 0);
             uint8_t* sa = smem + stage * STAGE_BYTES;
-            ig::tma_load_2d(sa, &tmA, &full[stage], kb * BK, a.a_row_base + m0 + tp.a_off[t]);
-            ig::tma_load_2d(sa + A_BYTES, &tmB, &full[stage], tp.b_off[t] + kb * BK, n0);
+            ig::tma_load_2d_cg2(sa, &tmA, bar, kb * BK, a.a_row_base + m0 + tp.a_off[t]);
+            ig::tma_load_2d_cg2(sa + A_BYTES, &tmB, bar, tp.b_off[t] + kb * BK, nb0);
             if (++stage == STAGES) {
               stage = 0;
               ph ^= 1;
@@ -146,14 +171,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = ig::umma_idesc_bf16(BM, a.block_n, 0, 0);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = ig::umma_idesc_bf16(PAIR_M, a.block_n, 0, 0);
       int stage = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
         const int phase = tile / tiles_per_phase;
         const Taps& tp = a.taps[phase];
         ig::mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -170,34 +195,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int krem = a.kc - kb * BK;
             const int nmma = krem >= BK ? BK / 16 : krem / 16;
             for (int k = 0; k < nmma; ++k) {
-              ig::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+              ig::umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
               accumulate = 1;
             }
-            ig::umma_commit(&empty[stage]);
+            ig::umma_commit_cg2(&empty[stage], 3);  // frees the stage in both CTAs
             if (++stage == STAGES) {
               stage = 0;
               ph ^= 1;
             }
           }
         }
-        ig::umma_commit(&tfull[acc]);
+        ig::umma_commit_cg2(&tfull[acc], 3);        // accumulator ready in both CTAs
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (both CTAs) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;      // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;       // which interleaved set of 16-column chunks
-    const int nchunks = a.block_n / 16;
+    const int half = ew >> 2;       // which interleaved set of column groups
+    uint8_t* stg = stg_base + ew * STG_BYTES;
+    constexpr bool OUT_F32 = (EPI == EPI_F32 || EPI == EPI_RESID || EPI == EPI_PATCH);
+    constexpr int ESZ = OUT_F32 ? 4 : 2;
+    constexpr int GC = OUT_F32 ? 32 : 64;   // columns per staged group = 128 bytes per row
+    constexpr int EPC = 16 / ESZ;           // elements per 16-byte chunk
+    const int ngroups = (a.block_n + GC - 1) / GC;
+    const uint32_t tempty_leader[2] = {ig::mapa_u32(&tempty[0], 0), ig::mapa_u32(&tempty[1], 0)};
     int acc = 0;
     uint32_t acc_ph = 0;
     int tile_par = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
       const int phase = tile / tiles_per_phase;
       const int rem = tile - phase * tiles_per_phase;
-      const int m0 = (rem / a.num_n_tiles) * BM;
+      const int m0 = (rem / a.num_n_tiles) * PAIR_M + static_cast<int>(rank) * BM;
       const int n0 = (rem % a.num_n_tiles) * a.block_n;
       const int row_in_tile = quad * 32 + lane;
       const int r = m0 + row_in_tile;
@@ -207,113 +238,153 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ig::tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * MAX_BN;
 
-      float logit[NCP];
-      if (EPI == EPI_FINAL) {
+      if (EPI != EPI_FINAL) {
+        // element offset of this thread's output row (+ n0), -1 = row is not stored
+        const bool store_row = (EPI == EPI_CONVT) ? ri.interior : ri.valid;
+        const long long obase = store_row ? static_cast<long long>(ri.orow) * a.ldo + n0 : -1ll;
+        bool released = false;
+        for (int g = half; g < ngroups; g += 2) {
+          const int col0 = g * GC;
+          const int gcols = (a.block_n - col0) < GC ? (a.block_n - col0) : GC;
+          uint32_t vr[GC];
 #pragma unroll
-        for (int k = 0; k < NCP; ++k) logit[k] = 0.f;
-      }
-
-      for (int ch = half; ch < nchunks; ch += 2) {
-        uint32_t vr[16];
-        ig::tmem_ld16(taddr0 + ch * 16, vr);
-        ig::tmem_ld_wait();
-        const int col = n0 + ch * 16;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
-
-        if (EPI == EPI_BF16) {
-          if (ri.valid) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float t = v[j] + (a.bias ? __ldg(a.bias + col + j) : 0.f);
-              v[j] = a.act ? ig::gelu_erf(t) : t;
-            }
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + ri.orow * a.ldo + col;
-            uint4 q0, q1;
-            q0.x = ig::pack_bf16(v[0], v[1]);   q0.y = ig::pack_bf16(v[2], v[3]);
-            q0.z = ig::pack_bf16(v[4], v[5]);   q0.w = ig::pack_bf16(v[6], v[7]);
-            q1.x = ig::pack_bf16(v[8], v[9]);   q1.y = ig::pack_bf16(v[10], v[11]);
-            q1.z = ig::pack_bf16(v[12], v[13]); q1.w = ig::pack_bf16(v[14], v[15]);
-            reinterpret_cast<uint4*>(o)[0] = q0;
-            reinterpret_cast<uint4*>(o)[1] = q1;
+          for (int u = 0; u < GC / 16; ++u)
+            if (u * 16 < gcols) ig::tmem_ld16p(taddr0 + col0 + u * 16, vr + u * 16);
+          ig::tmem_ld_wait();
+          if (g + 2 >= ngroups) {  // last TMEM read of this warp: hand the accumulator stage back early
+            ig::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ig::mbar_arrive_cluster(tempty_leader[acc]);
+            released = true;
           }
-        } else if (EPI == EPI_F32 || EPI == EPI_RESID || EPI == EPI_PATCH) {
-          if (ri.valid) {
-            float* o = static_cast<float*>(a.out) + ri.orow * a.ldo + col;
-            const float* rs = (EPI == EPI_RESID) ? a.resid + ri.orow * a.ldo + col : nullptr;
-            const float* ps = (EPI == EPI_PATCH) ? a.pos + static_cast<int64_t>(1 + ri.xx) * a.N + col : nullptr;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              float4 t = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-              if (a.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
-                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+          for (int u = 0; u < GC / 16; ++u) {
+            if (u * 16 < gcols) {
+              const int col = n0 + col0 + u * 16;
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[u * 16 + j]);
+              if (EPI == EPI_CONV) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
+                  const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + col) + j4);
+                  v[4 * j4 + 0] = fmaxf(fmaf(v[4 * j4 + 0], sc.x, sh.x), 0.f);
+                  v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc.y, sh.y), 0.f);
+                  v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc.z, sh.z), 0.f);
+                  v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], sc.w, sh.w), 0.f);
+                }
+                if (!ri.interior) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+              } else if (a.bias) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
+                  v[4 * j4 + 0] += b.x;
+                  v[4 * j4 + 1] += b.y;
+                  v[4 * j4 + 2] += b.z;
+                  v[4 * j4 + 3] += b.w;
+                }
               }
+              if (EPI == EPI_BF16 && a.act) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = ig::gelu_tanh3(v[j]);
+              }
+              if (OUT_F32) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                  *stg_slot(stg, lane, 4 * u + j4) =
+                      make_uint4(__float_as_uint(v[4 * j4]), __float_as_uint(v[4 * j4 + 1]),
+                                 __float_as_uint(v[4 * j4 + 2]), __float_as_uint(v[4 * j4 + 3]));
+              } else {
+                *stg_slot(stg, lane, 2 * u) =
+                    make_uint4(ig::pack_bf16(v[0], v[1]), ig::pack_bf16(v[2], v[3]),
+                               ig::pack_bf16(v[4], v[5]), ig::pack_bf16(v[6], v[7]));
+                *stg_slot(stg, lane, 2 * u + 1) =
+                    make_uint4(ig::pack_bf16(v[8], v[9]), ig::pack_bf16(v[10], v[11]),
+                               ig::pack_bf16(v[12], v[13]), ig::pack_bf16(v[14], v[15]));
+              }
+            }
+          }
+          __syncwarp();
+          // coalesced write-out: 8 lanes cover one 128-byte row piece, 4 rows per instruction
+          const int nchunk = gcols / EPC;
+          const int ch = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + (lane >> 3);
+            const long long ob = __shfl_sync(0xffffffffu, obase, row);
+            const int tok = (EPI == EPI_PATCH) ? __shfl_sync(0xffffffffu, ri.xx, row) : 0;
+            if (ob >= 0 && ch < nchunk) {
+              uint4 q = *stg_slot(stg, row, ch);
+              const long long off = ob + col0 + ch * EPC;
               if (EPI == EPI_RESID) {
-                const float4 b = reinterpret_cast<const float4*>(rs)[j4];
-                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+                const float4 rs = *reinterpret_cast<const float4*>(a.resid + off);
+                q.x = __float_as_uint(__uint_as_float(q.x) + rs.x);
+                q.y = __float_as_uint(__uint_as_float(q.y) + rs.y);
+                q.z = __float_as_uint(__uint_as_float(q.z) + rs.z);
+                q.w = __float_as_uint(__uint_as_float(q.w) + rs.w);
               }
               if (EPI == EPI_PATCH) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(ps) + j4);
-                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+                const float4 ps = __ldg(reinterpret_cast<const float4*>(
+                    a.pos + static_cast<int64_t>(1 + tok) * a.N + n0 + col0 + ch * EPC));
+                q.x = __float_as_uint(__uint_as_float(q.x) + ps.x);
+                q.y = __float_as_uint(__uint_as_float(q.y) + ps.y);
+                q.z = __float_as_uint(__uint_as_float(q.z) + ps.z);
+                q.w = __float_as_uint(__uint_as_float(q.w) + ps.w);
               }
-              reinterpret_cast<float4*>(o)[j4] = t;
+              if (OUT_F32)
+                *reinterpret_cast<uint4*>(static_cast<float*>(a.out) + off) = q;
+              else
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + off) = q;
             }
           }
-        } else if (EPI == EPI_CONV) {
-          if (ri.valid) {
+          __syncwarp();
+        }
+        if (!released) {  // warp had no column group in this tile (ngroups == 1, half == 1)
+          ig::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ig::mbar_arrive_cluster(tempty_leader[acc]);
+        }
+      } else {
+        // ---- EPI_FINAL: conv3x3 + BN + ReLU, then the 1x1 class conv and argmax in registers
+        float logit[NCP];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float t = fmaf(v[j], __ldg(a.bias + col + j), __ldg(a.shift + col + j));
-              v[j] = ri.interior ? fmaxf(t, 0.f) : 0.f;
-            }
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + ri.orow * a.ldo + col;
-            uint4 q0, q1;
-            q0.x = ig::pack_bf16(v[0], v[1]);   q0.y = ig::pack_bf16(v[2], v[3]);
-            q0.z = ig::pack_bf16(v[4], v[5]);   q0.w = ig::pack_bf16(v[6], v[7]);
-            q1.x = ig::pack_bf16(v[8], v[9]);   q1.y = ig::pack_bf16(v[10], v[11]);
-            q1.z = ig::pack_bf16(v[12], v[13]); q1.w = ig::pack_bf16(v[14], v[15]);
-            reinterpret_cast<uint4*>(o)[0] = q0;
-            reinterpret_cast<uint4*>(o)[1] = q1;
-          }
-        } else if (EPI == EPI_CONVT) {
-          if (ri.interior) {
+        for (int k = 0; k < NCP; ++k) logit[k] = 0.f;
+        const int nchunks = a.block_n / 16;
+        for (int ch = half; ch < nchunks; ch += 2) {
+          uint32_t vr[16];
+          ig::tmem_ld16(taddr0 + ch * 16, vr);
+          ig::tmem_ld_wait();
+          const int col = n0 + ch * 16;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(a.bias + col + j);
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + ri.orow * a.ldo + col;
-            uint4 q0, q1;
-            q0.x = ig::pack_bf16(v[0], v[1]);   q0.y = ig::pack_bf16(v[2], v[3]);
-            q0.z = ig::pack_bf16(v[4], v[5]);   q0.w = ig::pack_bf16(v[6], v[7]);
-            q1.x = ig::pack_bf16(v[8], v[9]);   q1.y = ig::pack_bf16(v[10], v[11]);
-            q1.z = ig::pack_bf16(v[12], v[13]); q1.w = ig::pack_bf16(v[14], v[15]);
-            reinterpret_cast<uint4*>(o)[0] = q0;
-            reinterpret_cast<uint4*>(o)[1] = q1;
-          }
-        } else if (EPI == EPI_FINAL) {
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + col) + j4);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float act = fmaxf(fmaf(v[j], __ldg(a.bias + col + j), __ldg(a.shift + col + j)), 0.f);
-            const float4* w4 = reinterpret_cast<const float4*>(w1s + (col + j) * NCP);
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = 4 * j4 + jj;
+              const float act = fmaxf(fmaf(__uint_as_float(vr[j]), scv[jj], shv[jj]), 0.f);
+              const float4* w4 = reinterpret_cast<const float4*>(w1s + (col + j) * NCP);
 #pragma unroll
-            for (int k4 = 0; k4 < NCP / 4; ++k4) {
-              const float4 w = w4[k4];
-              logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
-              logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
-              logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
-              logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
+              for (int k4 = 0; k4 < NCP / 4; ++k4) {
+                const float4 w = w4[k4];
+                logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
+                logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
+                logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
+                logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
+              }
             }
           }
         }
-      }
-      // accumulator fully read -> hand the TMEM stage back to the MMA warp
-      ig::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ig::mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1;
+        // accumulator fully read -> hand the TMEM stage back to the MMA warp
+        ig::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ig::mbar_arrive_cluster(tempty_leader[acc]);
 
-      if (EPI == EPI_FINAL) {
         float* ex = exch + (tile_par * BM + row_in_tile) * NCP;
         if (half == 1) {
 #pragma unroll
@@ -342,14 +413,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tile_par ^= 1;
       }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
     }
   }
 
+  // No CTA of the pair may exit (or free TMEM) while its peer can still read its shared memory,
+  // signal its barriers or write its accumulators.
   ig::tc_fence_before();
   __syncthreads();
+  ig::cluster_sync();
   if (warp == 1) {
     ig::tc_fence_after();
-    ig::tmem_dealloc(tmem_base, TMEM_COLS);
+    ig::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
   }
 }
 
@@ -363,9 +439,10 @@ static int launch_epi(const Plan& p, cudaStream_t stream) {
   }
   const int total = p.args.num_m_tiles * p.args.num_n_tiles * p.args.num_phases;
   if (total <= 0) return IG_OK;
-  const int grid = total < ig_num_sms() ? total : ig_num_sms();
+  const int max_pairs = ig_num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
   ig::ProfScope prof((EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) ? ig::PROF_GEMM_CONV : ig::PROF_GEMM_LINEAR, stream);
-  gemm_kernel<EPI><<<grid, THREADS, SMEM_TOTAL, stream>>>(p.tmA, p.tmB, p.args);
+  gemm_kernel<EPI><<<2 * pairs, THREADS, SMEM_TOTAL, stream>>>(p.tmA, p.tmB, p.args);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }
@@ -409,7 +486,7 @@ int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int
   a.N = N;
   a.block_n = pick_block_n(N);
   a.kc = K;
-  a.num_m_tiles = (M + BM - 1) / BM;
+  a.num_m_tiles = (M + PAIR_M - 1) / PAIR_M;
   a.num_n_tiles = N / a.block_n;
   a.num_phases = 1;
   a.a_row_base = 0;
@@ -419,7 +496,7 @@ int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int
   a.ldo = N;
   p->epi = epi;
   IG_TRY(ig_make_tmap_bf16(&p->tmA, A, M, K, lda, BM, BK));
-  IG_TRY(ig_make_tmap_bf16(&p->tmB, W, N, K, K, a.block_n, BK));
+  IG_TRY(ig_make_tmap_bf16(&p->tmB, W, N, K, K, a.block_n / 2, BK));
   return IG_OK;
 }
 

@@ -4,9 +4,10 @@
 
 namespace gemm {
 
-constexpr int BM = 128;      // rows per tile = TMEM lanes
+constexpr int BM = 128;      // rows per CTA = TMEM lanes
+constexpr int PAIR_M = 256;  // rows per CTA pair = one cta_group::2 UMMA tile
 constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle row of bf16
-constexpr int STAGES = 4;
+constexpr int STAGES = 5;
 constexpr int MAX_BN = 256;  // UMMA N limit
 constexpr int MAX_TAPS = 9;
 constexpr int NCP = 16;      // padded class count of the fused 1x1 head
@@ -31,7 +32,7 @@ struct Taps {
 
 struct Args {
   int M, N, block_n, kc;
-  int num_m_tiles, num_n_tiles, num_phases;
+  int num_m_tiles, num_n_tiles, num_phases;  // m tiles are PAIR_M rows
   int a_row_base;  // guard rows in front of A (keeps shifted TMA coordinates >= 0)
   Taps taps[4];
   const float* bias;   // bias, or BatchNorm scale for EPI_CONV / EPI_FINAL

@@ -371,7 +371,7 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
   a.N = Cout;
   a.block_n = gemm::pick_block_n(Cout);
   a.kc = Cin;
-  a.num_m_tiles = (a.M + gemm::BM - 1) / gemm::BM;
+  a.num_m_tiles = (a.M + gemm::PAIR_M - 1) / gemm::PAIR_M;
   a.num_n_tiles = Cout / a.block_n;
   a.a_row_base = in.guard;
   a.Hp = in.Hp;
@@ -408,7 +408,7 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
   p->epi = epi;
   IG_TRY(ig_make_tmap_bf16(&p->tmA, ws + in.off, in.rows, Cin, Cin, gemm::BM, gemm::BK));
   IG_TRY(ig_make_tmap_bf16(&p->tmB, w, Cout, 9 * static_cast<uint64_t>(Cin), 9 * static_cast<uint64_t>(Cin),
-                           a.block_n, gemm::BK));
+                           a.block_n / 2, gemm::BK));
   (void)m;
   return IG_OK;
 }

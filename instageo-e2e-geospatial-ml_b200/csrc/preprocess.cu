@@ -207,6 +207,7 @@ extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_sr
                              float* out_f32, void* out_patch, uint8_t* mask_elem, uint8_t* mask_px,
                              void* stream) {
   IG_TRY(ig_check_device());
+  if (n_win == 0 && n_img >= 0) return IG_OK;  // empty batch: torch hands out null pointers for 0-element tensors
   IG_REQUIRE(raw && band_idx && mean && std, IG_EINVAL, "ig_preprocess: null input pointer");
   IG_REQUIRE(raw_dtype == IG_I16 || raw_dtype == IG_U16 || raw_dtype == IG_F32 || raw_dtype == IG_F64, IG_EINVAL,
              "ig_preprocess: raw_dtype must be IG_I16, IG_U16, IG_F32 or IG_F64");
