@@ -234,6 +234,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int r = m0 + row_in_tile;
       const RowInfo ri = make_row<EPI>(a, r, phase);
 
+      if (EPI == EPI_RESID && ri.valid) {
+        // the residual tile does not depend on the MMAs: pull this thread's row pieces into L2 while
+        // the tensor core is still working on the tile
+        const float* rrow = a.resid + static_cast<long long>(ri.orow) * a.ldo + n0;
+        for (int g = half; g < ngroups; g += 2)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + g * GC));
+      }
       ig::mbar_wait(&tfull[acc], acc_ph);
       ig::tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * MAX_BN;
@@ -309,36 +316,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           __syncwarp();
-          // coalesced write-out: 8 lanes cover one 128-byte row piece, 4 rows per instruction
+          // coalesced write-out: 8 lanes cover one 128-byte row piece, 4 rows per instruction.
+          // All residual / pos-embed loads are issued before the first store: `out` may alias
+          // `resid`, so the compiler cannot hoist a later load above an earlier store itself, and
+          // a load -> add -> store chain per row would expose one DRAM latency per iteration.
           const int nchunk = gcols / EPC;
           const int ch = lane & 7;
+          long long offs[8];
+          float4 extra[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + (lane >> 3);
             const long long ob = __shfl_sync(0xffffffffu, obase, row);
             const int tok = (EPI == EPI_PATCH) ? __shfl_sync(0xffffffffu, ri.xx, row) : 0;
-            if (ob >= 0 && ch < nchunk) {
+            const bool ok = ob >= 0 && ch < nchunk;
+            offs[it] = ok ? ob + col0 + ch * EPC : -1ll;
+            extra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EPI_RESID && ok) extra[it] = *reinterpret_cast<const float4*>(a.resid + offs[it]);
+            if (EPI == EPI_PATCH && ok)
+              extra[it] = __ldg(reinterpret_cast<const float4*>(
+                  a.pos + static_cast<int64_t>(1 + tok) * a.N + n0 + col0 + ch * EPC));
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + (lane >> 3);
+            if (offs[it] >= 0) {
               uint4 q = *stg_slot(stg, row, ch);
-              const long long off = ob + col0 + ch * EPC;
-              if (EPI == EPI_RESID) {
-                const float4 rs = *reinterpret_cast<const float4*>(a.resid + off);
-                q.x = __float_as_uint(__uint_as_float(q.x) + rs.x);
-                q.y = __float_as_uint(__uint_as_float(q.y) + rs.y);
-                q.z = __float_as_uint(__uint_as_float(q.z) + rs.z);
-                q.w = __float_as_uint(__uint_as_float(q.w) + rs.w);
-              }
-              if (EPI == EPI_PATCH) {
-                const float4 ps = __ldg(reinterpret_cast<const float4*>(
-                    a.pos + static_cast<int64_t>(1 + tok) * a.N + n0 + col0 + ch * EPC));
-                q.x = __float_as_uint(__uint_as_float(q.x) + ps.x);
-                q.y = __float_as_uint(__uint_as_float(q.y) + ps.y);
-                q.z = __float_as_uint(__uint_as_float(q.z) + ps.z);
-                q.w = __float_as_uint(__uint_as_float(q.w) + ps.w);
+              if (EPI == EPI_RESID || EPI == EPI_PATCH) {
+                q.x = __float_as_uint(__uint_as_float(q.x) + extra[it].x);
+                q.y = __float_as_uint(__uint_as_float(q.y) + extra[it].y);
+                q.z = __float_as_uint(__uint_as_float(q.z) + extra[it].z);
+                q.w = __float_as_uint(__uint_as_float(q.w) + extra[it].w);
               }
               if (OUT_F32)
-                *reinterpret_cast<uint4*>(static_cast<float*>(a.out) + off) = q;
+                *reinterpret_cast<uint4*>(static_cast<float*>(a.out) + offs[it]) = q;
               else
-                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + off) = q;
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + offs[it]) = q;
             }
           }
           __syncwarp();

@@ -201,6 +201,36 @@ def probe_model():
         del m
 
 
+def probe_perf():
+    """Per-op device time at the bench shapes (V1-100M T=3 B=64 and V2-300M T=3 B=128)."""
+    for tag, M, D, H in [("v1_b64", 64 * 589, 768, 12), ("v2_b128", 128 * 589, 1024, 16)]:
+        x32 = torch.randn(M, D, device=dev)
+        xn = torch.randn(M, D, device=dev).bfloat16()
+        hid = torch.randn(M, 4 * D, device=dev).bfloat16()
+        wq = (torch.randn(3 * D, D, device=dev) * 0.02).bfloat16()
+        wp = (torch.randn(D, D, device=dev) * 0.02).bfloat16()
+        w1 = (torch.randn(4 * D, D, device=dev) * 0.02).bfloat16()
+        w2 = (torch.randn(D, 4 * D, device=dev) * 0.02).bfloat16()
+        bq, bp, b1 = (torch.randn(n, device=dev) for n in (3 * D, D, 4 * D))
+        gam, bet = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+        qkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+        ops_ = [
+            ("qkv", lambda: ops.linear(xn, wq, bq), 2 * M * D * 3 * D),
+            ("proj+resid", lambda: ops.linear(xn, wp, bp, resid=x32), 2 * M * D * D),
+            ("fc1+gelu", lambda: ops.linear(xn, w1, b1, act=1), 2 * M * D * 4 * D),
+            ("fc2+resid", lambda: ops.linear(hid, w2, bp, resid=x32), 2 * M * D * 4 * D),
+            ("attention", lambda: ops.attention(qkv, M // 589, 589, H), 4 * 589 * 589 * D * (M // 589)),
+            ("layernorm", lambda: ops.layernorm(x32, gam, bet), 0),
+        ]
+        tot = 0.0
+        for name, fn, fl in ops_:
+            ms = timeit(fn, iters=10)
+            tot += ms * (2 if name == "layernorm" else 1)
+            print(f"[perf {tag}] {name:11s} {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
+            RES[f"perf_{tag}_{name}"] = dict(us=ms * 1e3, tflops=fl / ms / 1e9)
+        print(f"[perf {tag}] block total {tot*1e3:.1f} us")
+
+
 def probe_bench():
     from instageo_b200.model import PrithviSeg
     for (variant, T, nc, B) in [("prithvi_eo_v1_100", 3, 13, 64)]:
@@ -214,7 +244,7 @@ def probe_bench():
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     fams = dict(gemm=probe_gemm, ln=probe_ln, attn=probe_attn, pre=probe_pre, stitch=probe_stitch,
-                model=probe_model, bench=probe_bench)
+                model=probe_model, perf=probe_perf, bench=probe_bench)
     t0 = time.time()
     try:
         for k, f in fams.items():
