@@ -45,7 +45,9 @@ constexpr int STG_BYTES = 32 * 128;               // per-warp transpose tile: 32
 constexpr int SMEM_STAGING = NUM_EPI_WARPS * STG_BYTES;  // 32768 (EPI_FINAL: cross-half logit exchange)
 constexpr int SMEM_W1 = MAX_BN * NCP * 4;         // 16384 (EPI_FINAL 1x1 weights)
 constexpr int SMEM_BARS = 256;                    // barriers + tmem ptr
-constexpr int SMEM_TOTAL = 1024 + SMEM_MAIN + SMEM_STAGING + SMEM_W1 + SMEM_BARS;
+constexpr int PC_COLS = MAX_BN / 2;               // columns one epilogue warp touches per tile
+constexpr int SMEM_PCACHE = NUM_EPI_WARPS * 2 * PC_COLS * 4;  // per-warp bias/scale + shift copies
+constexpr int SMEM_TOTAL = 1024 + SMEM_MAIN + SMEM_STAGING + SMEM_W1 + SMEM_BARS + SMEM_PCACHE;
 static_assert(2 * BM * NCP * 4 <= SMEM_STAGING, "logit exchange must fit the staging area");
 static_assert(SMEM_TOTAL <= 232448, "over the 227 KB shared-memory limit");
 
@@ -107,6 +109,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* pcache = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_STAGING + SMEM_W1 + SMEM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ig::cluster_ctarank();       // 0 = leader of the pair
@@ -220,7 +223,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int ESZ = OUT_F32 ? 4 : 2;
     constexpr int GC = OUT_F32 ? 32 : 64;   // columns per staged group = 128 bytes per row
     constexpr int EPC = 16 / ESZ;           // elements per 16-byte chunk
+    constexpr int GCX = (EPI == EPI_FINAL) ? 16 : GC;  // column-group width this warp interleaves by
+    constexpr bool HAS_SHIFT = (EPI == EPI_CONV || EPI == EPI_FINAL);
     const int ngroups = (a.block_n + GC - 1) / GC;
+    // Per-warp copy of the per-column epilogue parameters (bias | BN scale, BN shift) of the tile's
+    // columns this warp owns.  Filled with coalesced loads BEFORE waiting for the accumulator, read
+    // back as broadcast LDS.128: a global load per use sat on the critical path of every column
+    // group (L1 keeps ~14 KB next to 214 KB of shared memory and the streaming stores evict it).
+    float* pc0 = pcache + ew * 2 * PC_COLS;
+    float* pc1 = pc0 + PC_COLS;
     const uint32_t tempty_leader[2] = {ig::mapa_u32(&tempty[0], 0), ig::mapa_u32(&tempty[1], 0)};
     int acc = 0;
     uint32_t acc_ph = 0;
@@ -234,6 +245,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int r = m0 + row_in_tile;
       const RowInfo ri = make_row<EPI>(a, r, phase);
 
+      __syncwarp();
+      for (int idx = lane; idx < PC_COLS; idx += 32) {
+        const int c = (half + 2 * (idx / GCX)) * GCX + (idx % GCX);
+        if (c < a.block_n) {
+          pc0[idx] = a.bias ? __ldg(a.bias + n0 + c) : 0.f;
+          if (HAS_SHIFT) pc1[idx] = __ldg(a.shift + n0 + c);
+        }
+      }
+      __syncwarp();
       if (EPI == EPI_RESID && ri.valid) {
         // the residual tile does not depend on the MMAs: pull this thread's row pieces into L2 while
         // the tensor core is still working on the tile
@@ -267,15 +287,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int u = 0; u < GC / 16; ++u) {
             if (u * 16 < gcols) {
-              const int col = n0 + col0 + u * 16;
               float v[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[u * 16 + j]);
+              const int pci = (g >> 1) * GC + u * 16;  // this unit inside the warp's parameter cache
               if (EPI == EPI_CONV) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
-                  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
-                  const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + col) + j4);
+                  const float4 sc = *reinterpret_cast<const float4*>(pc0 + pci + 4 * j4);
+                  const float4 sh = *reinterpret_cast<const float4*>(pc1 + pci + 4 * j4);
                   v[4 * j4 + 0] = fmaxf(fmaf(v[4 * j4 + 0], sc.x, sh.x), 0.f);
                   v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc.y, sh.y), 0.f);
                   v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc.z, sh.z), 0.f);
@@ -285,10 +305,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
-              } else if (a.bias) {
+              } else {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
+                  const float4 b = *reinterpret_cast<const float4*>(pc0 + pci + 4 * j4);
                   v[4 * j4 + 0] += b.x;
                   v[4 * j4 + 1] += b.y;
                   v[4 * j4 + 2] += b.z;
@@ -372,10 +392,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           ig::tmem_ld16(taddr0 + ch * 16, vr);
           ig::tmem_ld_wait();
           const int col = n0 + ch * 16;
+          const int pci = (ch >> 1) * 16;
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bias + col) + j4);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + col) + j4);
+            const float4 sc = *reinterpret_cast<const float4*>(pc0 + pci + 4 * j4);
+            const float4 sh = *reinterpret_cast<const float4*>(pc1 + pci + 4 * j4);
             const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
