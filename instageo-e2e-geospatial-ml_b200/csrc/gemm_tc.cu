@@ -34,13 +34,9 @@
 
 namespace gemm {
 
-constexpr int A_BYTES = BM * BK * 2;              // 16384: this CTA's 128 rows
-constexpr int B_BYTES = (MAX_BN / 2) * BK * 2;    // 16384 reserved: this CTA's half of the B tile
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;   // 163840
 constexpr int STG_BYTES = 32 * 128;               // per-warp transpose tile: 32 rows x 128 B
 constexpr int SMEM_STAGING = NUM_EPI_WARPS * STG_BYTES;  // 32768 (EPI_FINAL: cross-half logit exchange)
 constexpr int SMEM_W1 = MAX_BN * NCP * 4;         // 16384 (EPI_FINAL 1x1 weights)
@@ -105,13 +101,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* w1s = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_STAGING);  // [N][NCP]
   float* exch = reinterpret_cast<float*>(stg_base);                         // [2][BM][NCP] (EPI_FINAL)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SMEM_MAIN + SMEM_STAGING + SMEM_W1);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tfull = empty + MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
   float* pcache = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_STAGING + SMEM_W1 + SMEM_BARS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = ig::cluster_ctarank();       // 0 = leader of the pair
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int tiles_per_phase = a.num_m_tiles * a.num_n_tiles;
@@ -122,7 +118,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     ig::tma_prefetch_desc(&tmA);
     ig::tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       ig::mbar_init(&full[s], 1);    // leader: its own expect_tx arrive; bytes from both CTAs
       ig::mbar_init(&empty[s], 1);   // one multicast commit per use
     }
@@ -143,14 +139,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ig::cluster_sync();  // peer barriers are initialised before anyone signals them
   ig::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (ig::elect_one()) {
       int stage = 0;
       uint32_t ph = 0;
-      const uint32_t tx_bytes = 2u * (A_BYTES + half_n * BK * 2);  // both CTAs' boxes
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         const int phase = tile / tiles_per_phase;
         const int rem = tile - phase * tiles_per_phase;
@@ -158,14 +153,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int nb0 = (rem % a.num_n_tiles) * a.block_n + static_cast<int>(rank) * half_n;
         const Taps& tp = a.taps[phase];
         for (int t = 0; t < tp.n; ++t) {
+          const TapGroup& tg = tp.g[t];
+          const uint32_t tx_bytes = 2u * (a.a_box_rows * BK * 2 + tg.nsub * half_n * BK * 2);  // both CTAs' boxes
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
             ig::mbar_wait(&empty[stage], ph ^ 1);
             if (rank == 0) ig::mbar_expect_tx(&full[stage], tx_bytes);
             const uint32_t bar = ig::mapa_u32(&full[stage], 0);
-            uint8_t* sa = smem + stage * STAGE_BYTES;
-            ig::tma_load_2d_cg2(sa, &tmA, bar, kb * BK, a.a_row_base + m0 + tp.a_off[t]);
-            ig::tma_load_2d_cg2(sa + A_BYTES, &tmB, bar, tp.b_off[t] + kb * BK, nb0);
-            if (++stage == STAGES) {
+            uint8_t* sa = smem + stage * a.stage_bytes;
+            ig::tma_load_2d_cg2(sa, &tmA, bar, kb * BK, a.a_row_base + m0 + tg.a_off);
+            for (int sb = 0; sb < tg.nsub; ++sb)
+              ig::tma_load_2d_cg2(sa + a.a_bytes + sb * a.b_tap_bytes, &tmB, bar, tg.b_off[sb] + kb * BK, nb0);
+            if (++stage == a.num_stages) {
               stage = 0;
               ph ^= 1;
             }
@@ -175,8 +173,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && lane == 0) {
+    // The whole warp walks the (uniform) loop and waits on the barriers; one elected lane issues.
+    // Everything the UMMAs consume is derived from uniform values, so the descriptors live in
+    // uniform registers: a single-lane loop made ptxas wrap every UTCHMMA in an ELECT / R2UR
+    // "waterfall" (~25 instructions per MMA) and the ISSUE rate, not the tensor pipe or L2,
+    // bounded the kernel at ~50 % tensor-pipe activity.
+    if (rank == 0) {
       const uint32_t idesc = ig::umma_idesc_bf16(PAIR_M, a.block_n, 0, 0);
+      const uint32_t smem_base = ig::smem_u32(smem);
       int stage = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -189,26 +193,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t d_tmem = tmem_base + acc * MAX_BN;
         uint32_t accumulate = 0;
         for (int t = 0; t < tp.n; ++t) {
+          const int nsub = tp.g[t].nsub;
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
             ig::mbar_wait(&full[stage], ph);
             ig::tc_fence_after();
-            const uint32_t sa = ig::smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t da = ig::umma_desc_sw128(sa, 1024, 16);
-            const uint64_t db = ig::umma_desc_sw128(sa + A_BYTES, 1024, 16);
+            const uint32_t sa = smem_base + stage * a.stage_bytes;
             const int krem = a.kc - kb * BK;
             const int nmma = krem >= BK ? BK / 16 : krem / 16;
-            for (int k = 0; k < nmma; ++k) {
-              ig::umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
-              accumulate = 1;
+            if (ig::elect_one()) {
+              for (int sb = 0; sb < nsub; ++sb) {
+                // row-shifted view of the shared A tile (start inside the swizzle atom, see ig_common.cuh)
+                const uint32_t a_lo = ig::umma_desc_lo(sa + tp.g[t].shift[sb] * 128);
+                const uint32_t b_lo = ig::umma_desc_lo(sa + a.a_bytes + sb * a.b_tap_bytes);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  if (k < nmma) {
+                    ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack(a_lo + 2 * k), ig::umma_desc_pack(b_lo + 2 * k),
+                                      idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+              }
+              ig::umma_commit_cg2(&empty[stage], 3);  // frees the stage in both CTAs
             }
-            ig::umma_commit_cg2(&empty[stage], 3);  // frees the stage in both CTAs
-            if (++stage == STAGES) {
+            __syncwarp();
+            accumulate = 1;
+            if (++stage == a.num_stages) {
               stage = 0;
               ph ^= 1;
             }
           }
         }
-        ig::umma_commit_cg2(&tfull[acc], 3);        // accumulator ready in both CTAs
+        if (ig::elect_one()) ig::umma_commit_cg2(&tfull[acc], 3);  // accumulator ready in both CTAs
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
       }
@@ -487,6 +504,8 @@ int launch(const Plan& p, cudaStream_t stream) {
              "gemm: block_n=%d must be a multiple of 16 in [16,256]", a.block_n);
   IG_REQUIRE(a.kc >= 16 && a.kc % 16 == 0, IG_ESHAPE, "gemm: K per tap %d must be a multiple of 16", a.kc);
   IG_REQUIRE(a.N % a.block_n == 0, IG_ESHAPE, "gemm: N=%d not a multiple of block_n=%d", a.N, a.block_n);
+  IG_REQUIRE(a.num_stages >= 2 && a.num_stages * a.stage_bytes <= SMEM_MAIN, IG_ESHAPE,
+             "gemm: operand ring does not fit (stage %d B x %d)", a.stage_bytes, a.num_stages);
   switch (p.epi) {
     case EPI_BF16: return launch_epi<EPI_BF16>(p, stream);
     case EPI_F32: return launch_epi<EPI_F32>(p, stream);
@@ -501,6 +520,18 @@ int launch(const Plan& p, cudaStream_t stream) {
   }
   ig_set_error("gemm: unknown epilogue %d", p.epi);
   return IG_EINVAL;
+}
+
+void finish_geometry(Args* a) {
+  int maxsub = 1;
+  for (int ph = 0; ph < a->num_phases; ++ph)
+    for (int t = 0; t < a->taps[ph].n; ++t)
+      if (a->taps[ph].g[t].nsub > maxsub) maxsub = a->taps[ph].g[t].nsub;
+  a->a_bytes = (a->a_box_rows * BK * 2 + 1023) / 1024 * 1024;
+  a->b_tap_bytes = ((a->block_n / 2) * BK * 2 + 1023) / 1024 * 1024;
+  a->stage_bytes = a->a_bytes + maxsub * a->b_tap_bytes;
+  a->num_stages = SMEM_MAIN / a->stage_bytes;
+  if (a->num_stages > MAX_STAGES) a->num_stages = MAX_STAGES;
 }
 
 int pick_block_n(int N) {
@@ -524,12 +555,16 @@ int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int
   a.num_n_tiles = N / a.block_n;
   a.num_phases = 1;
   a.a_row_base = 0;
+  a.a_box_rows = BM;
   a.taps[0].n = 1;
-  a.taps[0].a_off[0] = 0;
-  a.taps[0].b_off[0] = 0;
+  a.taps[0].g[0].a_off = 0;
+  a.taps[0].g[0].nsub = 1;
+  a.taps[0].g[0].shift[0] = 0;
+  a.taps[0].g[0].b_off[0] = 0;
   a.ldo = N;
+  finish_geometry(&a);
   p->epi = epi;
-  IG_TRY(ig_make_tmap_bf16(&p->tmA, A, M, K, lda, BM, BK));
+  IG_TRY(ig_make_tmap_bf16(&p->tmA, A, M, K, lda, a.a_box_rows, BK));
   IG_TRY(ig_make_tmap_bf16(&p->tmB, W, N, K, K, a.block_n / 2, BK));
   return IG_OK;
 }

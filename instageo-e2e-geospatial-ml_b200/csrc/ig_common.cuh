@@ -93,9 +93,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging
-// the GPU.  ~4 s budget, far above any kernel in this library.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// the GPU.  ~4 s budget, far above any kernel in this library.  The spin loop lives out of line
+// so the hot path (barrier already complete) is a single try_wait.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   unsigned long long t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -110,6 +110,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
+}
+// One lane of a converged warp (elect.sync): the issuing lane of TMA / tcgen05 instructions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Warp index as a value the compiler KNOWS is warp-uniform (shuffle broadcast), so role branches are
+// uniform branches and descriptor arithmetic stays on the uniform datapath.
+__device__ __forceinline__ int warp_idx_uniform() {
+  return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
 }
 
 // ---- proxies / fences
@@ -157,6 +176,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 //   [46,48) version = 1, [49,52) base offset, [61,64) layout type (2 = SWIZZLE_128B).
 // K-major operand: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO); LBO unused.
 // MN-major operand (64 MN elements wide): rows are K, 8-row K groups 1024 B apart (SBO).
+// The base-offset field [49,52) stays 0 even when the operand starts INSIDE a 1024-byte swizzle atom
+// (row-shifted taps of the implicit-GEMM convolution start at tile + shift*128 B): measured on B200,
+// the 128-byte swizzle XOR is applied to absolute shared-memory address bits, so a shifted start reads
+// exactly the rows TMA wrote; setting base_offset = (addr >> 7) & 7 produced wrong operands.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes,
                                                     uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -169,6 +192,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 }
 // Instruction descriptor: c=f32 (bits 4-5 = 1), a=b=bf16 (bits 7-9, 10-12 = 1),
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at 17, M>>4 at 24.
+// Same descriptor as (lo, hi) words: only `lo` changes inside a K loop (start address >> 4, +2 per
+// 16 bf16 of K), `hi` is the constant SBO=1024 | version 1 | SWIZZLE_128B word.
+constexpr uint32_t UMMA_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(UMMA_DESC_HI_SW128));
+  return d;
+}
 __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn,
                                                     uint32_t b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) |

@@ -7,9 +7,12 @@ namespace gemm {
 constexpr int BM = 128;      // rows per CTA = TMEM lanes
 constexpr int PAIR_M = 256;  // rows per CTA pair = one cta_group::2 UMMA tile
 constexpr int BK = 64;       // K per pipeline stage = one 128-byte swizzle row of bf16
-constexpr int STAGES = 5;
+constexpr int MAX_STAGES = 8; // pipeline depth = SMEM_MAIN / stage bytes, at most this
+constexpr int SMEM_MAIN = 160 * 1024;  // operand ring
 constexpr int MAX_BN = 256;  // UMMA N limit
-constexpr int MAX_TAPS = 9;
+constexpr int MAX_GROUPS = 3;  // A tiles per accumulation phase (vertical taps dy)
+constexpr int MAX_SUB = 3;     // taps that share one A tile (horizontal taps dx = row shifts 0..2)
+constexpr int A_HALO = 8;      // extra rows loaded after the 128 so shifted taps stay inside the tile
 constexpr int NCP = 16;      // padded class count of the fused 1x1 head
 
 enum Epi {
@@ -23,17 +26,27 @@ enum Epi {
   EPI_COUNT = 7
 };
 
-// One accumulation phase = a list of (A row shift, B column offset) taps, each `kc` wide.
+// One accumulation phase = up to MAX_GROUPS shared A tiles; each is loaded ONCE per K block
+// (rows a_off .. a_off + 128 + A_HALO relative to the output tile) and used by `nsub` taps that
+// read it at row shift `shift[s]` (UMMA descriptor start + shift*128 B) against B columns b_off[s].
+// A 3x3 convolution is 3 groups (dy) x 3 sub-taps (dx): A traffic drops 3x versus one load per tap.
+struct TapGroup {
+  int a_off;
+  int nsub;
+  int shift[MAX_SUB];
+  int b_off[MAX_SUB];
+};
 struct Taps {
   int n;
-  int a_off[MAX_TAPS];
-  int b_off[MAX_TAPS];
+  TapGroup g[MAX_GROUPS];
 };
 
 struct Args {
   int M, N, block_n, kc;
   int num_m_tiles, num_n_tiles, num_phases;  // m tiles are PAIR_M rows
   int a_row_base;  // guard rows in front of A (keeps shifted TMA coordinates >= 0)
+  int a_box_rows;  // rows per A TMA box: 128, or 128 + A_HALO when taps are row-shifted
+  int a_bytes, b_tap_bytes, stage_bytes, num_stages;  // operand ring geometry (host-computed)
   Taps taps[4];
   const float* bias;   // bias, or BatchNorm scale for EPI_CONV / EPI_FINAL
   const float* shift;  // BatchNorm shift (with conv bias folded)
@@ -64,5 +77,7 @@ int launch(const Plan& p, cudaStream_t stream);
 // Plain linear: A [M,K] bf16 row-major (lda elements), W [N,K] bf16 row-major.
 int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int M, int N, int K);
 int pick_block_n(int N);
+// fills a_bytes / b_tap_bytes / stage_bytes / num_stages from block_n, a_box_rows and the tap lists
+void finish_geometry(Args* a);
 
 }  // namespace gemm

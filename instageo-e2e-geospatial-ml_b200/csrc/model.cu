@@ -377,16 +377,23 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
   a.Hp = in.Hp;
   a.Wp = in.Wp;
   a.ldo = Cout;
+  a.a_box_rows = gemm::BM + gemm::A_HALO;
   if (!transposed) {
+    // 3 A tiles (dy = -1, 0, 1), each shared by the 3 horizontal taps dx = -1, 0, 1 (row shifts 0, 1, 2)
     a.num_phases = 1;
-    a.taps[0].n = 9;
-    for (int ky = 0; ky < 3; ++ky)
+    a.taps[0].n = 3;
+    for (int ky = 0; ky < 3; ++ky) {
+      gemm::TapGroup& g = a.taps[0].g[ky];
+      g.a_off = (ky - 1) * in.Wp - 1;
+      g.nsub = 3;
       for (int kx = 0; kx < 3; ++kx) {
-        a.taps[0].a_off[ky * 3 + kx] = (ky - 1) * in.Wp + (kx - 1);
-        a.taps[0].b_off[ky * 3 + kx] = (ky * 3 + kx) * Cin;
+        g.shift[kx] = kx;
+        g.b_off[kx] = (ky * 3 + kx) * Cin;
       }
+    }
   } else {
-    // out[2y+pa, 2x+pb]: pa=0 -> (ky=1, dy=0); pa=1 -> (ky=2, dy=0), (ky=0, dy=1); same along x
+    // out[2y+pa, 2x+pb]: pa=0 -> (ky=1, dy=0); pa=1 -> (ky=2, dy=0), (ky=0, dy=1); same along x.
+    // One A tile per dy, shared by the dx = 0, 1 taps (row shifts 0, 1).
     a.num_phases = 4;
     for (int pa = 0; pa < 2; ++pa)
       for (int pb = 0; pb < 2; ++pb) {
@@ -394,19 +401,23 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
         a.phase_a[ph] = pa;
         a.phase_b[ph] = pb;
         gemm::Taps& t = a.taps[ph];
-        t.n = 0;
-        const int kys[2] = {pa ? 2 : 1, 0}, dys[2] = {0, 1};
-        const int kxs[2] = {pb ? 2 : 1, 0}, dxs[2] = {0, 1};
-        for (int iy = 0; iy < (pa ? 2 : 1); ++iy)
-          for (int ix = 0; ix < (pb ? 2 : 1); ++ix) {
-            t.a_off[t.n] = dys[iy] * in.Wp + dxs[ix];
-            t.b_off[t.n] = (kys[iy] * 3 + kxs[ix]) * Cin;
-            ++t.n;
+        t.n = pa ? 2 : 1;
+        const int kys[2] = {pa ? 2 : 1, 0};
+        const int kxs[2] = {pb ? 2 : 1, 0};
+        for (int iy = 0; iy < t.n; ++iy) {
+          gemm::TapGroup& g = t.g[iy];
+          g.a_off = iy * in.Wp;
+          g.nsub = pb ? 2 : 1;
+          for (int ix = 0; ix < g.nsub; ++ix) {
+            g.shift[ix] = ix;
+            g.b_off[ix] = (kys[iy] * 3 + kxs[ix]) * Cin;
           }
+        }
       }
   }
+  gemm::finish_geometry(&a);
   p->epi = epi;
-  IG_TRY(ig_make_tmap_bf16(&p->tmA, ws + in.off, in.rows, Cin, Cin, gemm::BM, gemm::BK));
+  IG_TRY(ig_make_tmap_bf16(&p->tmA, ws + in.off, in.rows, Cin, Cin, a.a_box_rows, gemm::BK));
   IG_TRY(ig_make_tmap_bf16(&p->tmB, w, Cout, 9 * static_cast<uint64_t>(Cin), 9 * static_cast<uint64_t>(Cin),
                            a.block_n / 2, gemm::BK));
   (void)m;
