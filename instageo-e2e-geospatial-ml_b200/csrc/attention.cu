@@ -6,15 +6,19 @@
 // reshape/permute of the reference costs nothing: Q, K and V tiles are 2-D TMA boxes of that
 // matrix.  Output is written as [B*N, D] (head-major), the exact operand of the proj GEMM.
 //
-// One CTA = 128 query rows of one (batch, head).  tcgen05 throughout:
-//   S = Q K^T   : UMMA 128x128x16, both operands K-major (128-byte swizzle), S in TMEM
-//   O += P V    : UMMA 128x64x16, A = P (bf16, written to smem by the softmax warps),
-//                 B = V used MN-major straight from its [kv, 64] tile (no transpose pass)
-// Softmax: thread <-> TMEM lane <-> query row, so row max / row sum are thread-local.
-// Two passes over the KV blocks: pass 0 finds the exact row max (QK^T only), pass 1
-// recomputes S, exponentiates against the final max and accumulates P V in TMEM -- no
-// accumulator rescaling, at the price of issuing the (cheap) QK^T MMAs twice.
-// 96 KB smem + 256 TMEM columns per CTA -> 2 CTAs per SM overlap softmax with MMA.
+// One CTA = 128 query rows of one (batch, head); 2 CTAs per SM.  tcgen05 throughout:
+//   S   = Q K_j^T : UMMA 128x128x16, both operands K-major (128-byte swizzle), S in TMEM
+//   O_j = P_j V_j : UMMA 128x64x16, A = P_j (bf16, written to swizzled smem by the softmax warps),
+//                   B = V_j used MN-major straight from its [kv, 64] tile (no transpose pass);
+//                   NOT accumulated in TMEM: each block's product lands in its own TMEM buffer
+// Softmax (4 warps, thread <-> TMEM lane <-> query row): single pass over the KV blocks with a
+// running max.  Per block: read S once for the row max, read it again to exponentiate against the
+// new max (TMEM reads are cheap, a second QK^T is not needed), write P_j; then fold the PREVIOUS
+// block's O_{j-1} into register accumulators: acc = acc * exp(m_{j-2} - m_{j-1}) + O_{j-1}.
+// Keeping the running output in registers means no TMEM read-modify-write rescale and no ordering
+// hazard between the rescale and the next P V MMA: the tensor core only ever writes fresh tiles.
+// TMEM loads are software-pipelined (the next 32-column chunk is in flight while the current one
+// is processed).  The exp count (N^2 per head) on the 16-lane/clk MUFU is the floor of this kernel.
 #include "ig_ops.cuh"
 
 namespace attn {
@@ -26,10 +30,13 @@ constexpr int OFF_K = OFF_Q + TILE_BYTES;       // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;   // 1 stage
 constexpr int OFF_P = OFF_V + TILE_BYTES;       // 128 x 128 bf16 = two 128x64 swizzle atoms
 constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr int SMEM_TOTAL = 1024 + OFF_BAR + 128;
+constexpr int SMEM_TOTAL = 1024 + OFF_BAR + 256;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128;
+constexpr int COL_S = 0, COL_O = 128;           // O buffers at 128 and 192
+
+// 32 columns of one TMEM lane quadrant -> registers (asynchronous until tmem_ld_wait)
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) { ig::tmem_ld32(taddr, v); }
 
 __global__ void __launch_bounds__(THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int D) {
@@ -43,13 +50,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
   uint64_t* v_full = bars + 5;
   uint64_t* v_empty = bars + 6;
   uint64_t* s_full = bars + 7;
-  uint64_t* s_empty = bars + 8;
+  uint64_t* s_free = bars + 8;
   uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* p_free = bars + 10;
+  uint64_t* o_full = bars + 11;  // [2]
+  uint64_t* o_free = bars + 13;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nb = (N + BKV - 1) / BKV;
   const int row0 = b * N;  // first token row of this batch element in the qkv matrix
@@ -60,14 +68,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
     for (int s = 0; s < 2; ++s) {
       ig::mbar_init(&k_full[s], 1);
       ig::mbar_init(&k_empty[s], 1);
+      ig::mbar_init(&o_full[s], 1);
+      ig::mbar_init(&o_free[s], 4);
     }
     ig::mbar_init(v_full, 1);
     ig::mbar_init(v_empty, 1);
     ig::mbar_init(s_full, 1);
-    ig::mbar_init(s_empty, 4);
+    ig::mbar_init(s_free, 4);
     ig::mbar_init(p_full, 4);
-    ig::mbar_init(p_empty, 1);
-    ig::mbar_init(o_full, 1);
+    ig::mbar_init(p_free, 1);
     ig::fence_barrier_init();
   }
   if (warp == 1) {
@@ -77,44 +86,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
   ig::tc_fence_before();
   __syncthreads();
   ig::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ig::elect_one()) {
       // ===================== TMA producer =====================
       ig::mbar_expect_tx(q_full, TILE_BYTES);
       ig::tma_load_2d(smem + OFF_Q, &tm, q_full, h * HD, row0 + q0);
-      int kit = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < nb; ++j, ++kit) {
-          const int st = kit & 1;
-          ig::mbar_wait(&k_empty[st], ((kit >> 1) & 1) ^ 1);
-          ig::mbar_expect_tx(&k_full[st], TILE_BYTES);
-          ig::tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tm, &k_full[st], D + h * HD, row0 + j * BKV);
-          if (pass == 1) {
-            ig::mbar_wait(v_empty, (j & 1) ^ 1);
-            ig::mbar_expect_tx(v_full, TILE_BYTES);
-            ig::tma_load_2d(smem + OFF_V, &tm, v_full, 2 * D + h * HD, row0 + j * BKV);
-          }
-        }
+      for (int j = 0; j < nb; ++j) {
+        const int st = j & 1;
+        ig::mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        ig::mbar_expect_tx(&k_full[st], TILE_BYTES);
+        ig::tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tm, &k_full[st], D + h * HD, row0 + j * BKV);
+        ig::mbar_wait(v_empty, (j & 1) ^ 1);
+        ig::mbar_expect_tx(v_full, TILE_BYTES);
+        ig::tma_load_2d(smem + OFF_V, &tm, v_full, 2 * D + h * HD, row0 + j * BKV);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc_s = ig::umma_idesc_bf16(BQ, BKV, 0, 0);
-      const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V, MN-major
-      const uint32_t sq = ig::smem_u32(smem + OFF_Q);
-      const uint32_t sp = ig::smem_u32(smem + OFF_P);
-      const uint32_t sv = ig::smem_u32(smem + OFF_V);
-      ig::mbar_wait(q_full, 0);
-      int kit = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < nb; ++j, ++kit) {
-          const int st = kit & 1;
-          ig::mbar_wait(&k_full[st], (kit >> 1) & 1);
-          ig::mbar_wait(s_empty, (kit & 1) ^ 1);
-          ig::tc_fence_after();
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    const uint32_t idesc_s = ig::umma_idesc_bf16(BQ, BKV, 0, 0);
+    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V, MN-major
+    const uint32_t sq = ig::smem_u32(smem + OFF_Q);
+    const uint32_t sp = ig::smem_u32(smem + OFF_P);
+    const uint32_t sv = ig::smem_u32(smem + OFF_V);
+    ig::mbar_wait(q_full, 0);
+    for (int j = 0; j <= nb; ++j) {
+      if (j < nb) {
+        const int st = j & 1;
+        ig::mbar_wait(&k_full[st], (j >> 1) & 1);
+        ig::mbar_wait(s_free, (j & 1) ^ 1);
+        ig::tc_fence_after();
+        if (ig::elect_one()) {
           const uint64_t dq = ig::umma_desc_sw128(sq, 1024, 16);
           const uint64_t dk = ig::umma_desc_sw128(ig::smem_u32(smem + OFF_K + st * TILE_BYTES), 1024, 16);
 #pragma unroll
@@ -122,24 +125,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
             ig::umma_bf16(tmem_base + COL_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
           ig::umma_commit(s_full);
           ig::umma_commit(&k_empty[st]);
-          if (pass == 1) {
-            ig::mbar_wait(v_full, j & 1);
-            ig::mbar_wait(p_full, j & 1);
-            ig::tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < BKV / 16; ++k) {
-              // A = P: atom (k / 4) of 128 rows x 64 kv, 32 bytes per K step inside the atom
-              const uint64_t dp = ig::umma_desc_sw128(sp + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16);
-              // B = V (MN-major): 16 kv rows of 128 bytes per K step, 8-row groups 1024 B apart
-              const uint64_t dv = ig::umma_desc_sw128(sv + k * 2048, 1024, 1024);
-              ig::umma_bf16(tmem_base + COL_O, dp, dv, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-            }
-            ig::umma_commit(v_empty);
-            ig::umma_commit(p_empty);
-          }
         }
+        __syncwarp();
       }
-      ig::umma_commit(o_full);
+      if (j > 0) {
+        const int jj = j - 1, ob = jj & 1;  // O_jj = P_jj V_jj into its own buffer
+        ig::mbar_wait(v_full, jj & 1);
+        ig::mbar_wait(p_full, jj & 1);
+        ig::mbar_wait(&o_free[ob], ((jj >> 1) & 1) ^ 1);
+        ig::tc_fence_after();
+        if (ig::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A = P: atom (k / 4) of 128 rows x 64 kv, 32 bytes per K step inside the atom
+            const uint64_t dp = ig::umma_desc_sw128(sp + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16);
+            // B = V (MN-major): 16 kv rows of 128 bytes per K step, 8-row groups 1024 B apart
+            const uint64_t dv = ig::umma_desc_sw128(sv + k * 2048, 1024, 1024);
+            ig::umma_bf16(tmem_base + COL_O + ob * HD, dp, dv, idesc_o, k > 0);
+          }
+          ig::umma_commit(&o_full[ob]);
+          ig::umma_commit(v_empty);
+          ig::umma_commit(p_free);
+        }
+        __syncwarp();
+      }
     }
   } else {
     // ===================== softmax / output warps (one thread per query row) =====================
@@ -148,43 +157,61 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + COL_S;
     const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + COL_O;
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-    int sit = 0;
-    float m = -INFINITY;
-    for (int j = 0; j < nb; ++j, ++sit) {
-      ig::mbar_wait(s_full, sit & 1);
-      ig::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ig::tmem_ld32(t_s + c * 32, v);
-        ig::tmem_ld_wait();
-        const int col0 = j * BKV + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) m = fmaxf(m, __uint_as_float(v[i]));
-      }
-      ig::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ig::mbar_arrive(s_empty);
-    }
-    const float mc = (m == -INFINITY) ? 0.f : m * sl2;
-    float l = 0.f;
     uint8_t* prow = smem + OFF_P + row * 128;
-    for (int j = 0; j < nb; ++j, ++sit) {
-      ig::mbar_wait(s_full, sit & 1);
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    float m_ref = -INFINITY, l = 0.f, alpha_pend = 0.f;
+    uint32_t va[32], vb[32];
+
+    for (int j = 0; j < nb; ++j) {
+      const int kv0 = j * BKV;
+      const bool tail = kv0 + BKV > N;  // block has masked columns
+      ig::mbar_wait(s_full, j & 1);
       ig::tc_fence_after();
-      ig::mbar_wait(p_empty, (j & 1) ^ 1);
+      // ---- pass A: row max (next chunk in flight while the current one is reduced)
+      float mb = -INFINITY;
+      ld32(t_s, va);
+      ig::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ig::tmem_ld32(t_s + c * 32, v);
+        uint32_t(&cur)[32] = (c & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+        if (c < 3) ld32(t_s + (c + 1) * 32, nxt);
+        else ld32(t_s, nxt);  // first chunk of pass B
+        const int col0 = kv0 + c * 32;
+        if (!tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mb = fmaxf(mb, __uint_as_float(cur[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) mb = fmaxf(mb, __uint_as_float(cur[i]));
+        }
         ig::tmem_ld_wait();
-        const int col0 = j * BKV + c * 32;
+      }
+      const float m_new = fmaxf(m_ref, mb);
+      const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 0 on the first block
+      const float mc = m_new * sl2;
+      m_ref = m_new;
+      l *= alpha;
+      // ---- pass B: exponentials -> P (bf16, swizzled smem); chunk 0 is already in `va`
+      ig::mbar_wait(p_free, (j & 1) ^ 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t(&cur)[32] = (c & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+        if (c < 3) ld32(t_s + (c + 1) * 32, nxt);
+        const int col0 = kv0 + c * 32;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = (col0 + 2 * i < N) ? ig::ex2(fmaf(__uint_as_float(v[2 * i]), sl2, -mc)) : 0.f;
-          const float p1 = (col0 + 2 * i + 1 < N) ? ig::ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -mc)) : 0.f;
+          float p0 = ig::ex2(fmaf(__uint_as_float(cur[2 * i]), sl2, -mc));
+          float p1 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -mc));
+          if (tail) {
+            p0 = (col0 + 2 * i < N) ? p0 : 0.f;
+            p1 = (col0 + 2 * i + 1 < N) ? p1 : 0.f;
+          }
           l += p0 + p1;
           pk[i] = ig::pack_bf16(p0, p1);
         }
@@ -195,35 +222,59 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
           *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
+        if (c < 3) ig::tmem_ld_wait();
       }
       ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
       ig::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         ig::mbar_arrive(p_full);
-        ig::mbar_arrive(s_empty);
+        ig::mbar_arrive(s_free);
+      }
+      // ---- fold the previous block's O into the register accumulators
+      if (j > 0) {
+        const int jj = j - 1, ob = jj & 1;
+        ig::mbar_wait(&o_full[ob], (jj >> 1) & 1);
+        ig::tc_fence_after();
+        ld32(t_o + ob * HD, va);
+        ld32(t_o + ob * HD + 32, vb);
+        ig::tmem_ld_wait();
+        ig::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ig::mbar_arrive(&o_free[ob]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          acc[i] = fmaf(acc[i], alpha_pend, __uint_as_float(va[i]));
+          acc[32 + i] = fmaf(acc[32 + i], alpha_pend, __uint_as_float(vb[i]));
+        }
+      }
+      alpha_pend = alpha;
+    }
+    {
+      const int jj = nb - 1, ob = jj & 1;
+      ig::mbar_wait(&o_full[ob], (jj >> 1) & 1);
+      ig::tc_fence_after();
+      ld32(t_o + ob * HD, va);
+      ld32(t_o + ob * HD + 32, vb);
+      ig::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] = fmaf(acc[i], alpha_pend, __uint_as_float(va[i]));
+        acc[32 + i] = fmaf(acc[32 + i], alpha_pend, __uint_as_float(vb[i]));
       }
     }
-    ig::mbar_wait(o_full, 0);
-    ig::tc_fence_after();
     const float inv = 1.f / l;
     const int qrow = q0 + row;
-    __nv_bfloat16* orow = out + (static_cast<int64_t>(row0) + qrow) * D + h * HD;
+    if (qrow < N) {
+      __nv_bfloat16* orow = out + (static_cast<int64_t>(row0) + qrow) * D + h * HD;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      ig::tmem_ld32(t_o + c * 32, v);
-      ig::tmem_ld_wait();
-      if (qrow < N) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = ig::pack_bf16(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
-          o.y = ig::pack_bf16(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
-          o.z = ig::pack_bf16(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
-          o.w = ig::pack_bf16(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
-          reinterpret_cast<uint4*>(orow + c * 32)[q] = o;
-        }
+      for (int q = 0; q < 8; ++q) {
+        uint4 o;
+        o.x = ig::pack_bf16(acc[8 * q + 0] * inv, acc[8 * q + 1] * inv);
+        o.y = ig::pack_bf16(acc[8 * q + 2] * inv, acc[8 * q + 3] * inv);
+        o.z = ig::pack_bf16(acc[8 * q + 4] * inv, acc[8 * q + 5] * inv);
+        o.w = ig::pack_bf16(acc[8 * q + 6] * inv, acc[8 * q + 7] * inv);
+        reinterpret_cast<uint4*>(orow)[q] = o;
       }
     }
   }
