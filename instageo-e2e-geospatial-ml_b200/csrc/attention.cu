@@ -7,55 +7,59 @@
 // matrix.  Output is written as [B*N, D] (head-major), the exact operand of the proj GEMM.
 //
 // One CTA = 128 query rows of one (batch, head); 2 CTAs per SM.  tcgen05 throughout:
-//   S   = Q K_j^T : UMMA 128x128x16, both operands K-major (128-byte swizzle), S in TMEM
+//   S_j = Q K_j^T : UMMA 128x64x16, both operands K-major (128-byte swizzle), S double-buffered in TMEM
 //   O_j = P_j V_j : UMMA 128x64x16, A = P_j (bf16, written to swizzled smem by the softmax warps),
 //                   B = V_j used MN-major straight from its [kv, 64] tile (no transpose pass);
 //                   NOT accumulated in TMEM: each block's product lands in its own TMEM buffer
-// Softmax (4 warps, thread <-> TMEM lane <-> query row): single pass over the KV blocks with a
-// running max.  Per block: read S once for the row max, read it again to exponentiate against the
-// new max (TMEM reads are cheap, a second QK^T is not needed), write P_j; then fold the PREVIOUS
-// block's O_{j-1} into register accumulators: acc = acc * exp(m_{j-2} - m_{j-1}) + O_{j-1}.
+// KV blocks are 64 wide so that two S tiles and two O tiles fit the CTA's 256 TMEM columns: the
+// tensor core computes S_{j+1}/S_{j+2} while the softmax warps work on S_j, and they never wait for it.
+// Softmax (4 warps, thread <-> TMEM lane <-> query row): single pass with a running max.  Per block the
+// 64 scores of the row are pulled into registers once (the S buffer is released immediately), reduced
+// to the new max, exponentiated against it (masked columns are -inf -> 0), written as P_j; then the
+// PREVIOUS block's O_{j-1} is folded into register accumulators:
+//   acc = acc * exp(m_{j-2} - m_{j-1}) + O_{j-1}.
 // Keeping the running output in registers means no TMEM read-modify-write rescale and no ordering
-// hazard between the rescale and the next P V MMA: the tensor core only ever writes fresh tiles.
-// TMEM loads are software-pipelined (the next 32-column chunk is in flight while the current one
-// is processed).  The exp count (N^2 per head) on the 16-lane/clk MUFU is the floor of this kernel.
+// hazard between a rescale and the next P V MMA: the tensor core only ever writes fresh tiles.
+// Max / sum reductions use 4 independent chains (a single dependent FADD/FMNMX chain per row cost as
+// much as the exponentials).  The exp count (N^2 per head) on the 16-lane/clk MUFU is the floor.
 #include "ig_ops.cuh"
 
 namespace attn {
 
-constexpr int BQ = 128, BKV = 128, HD = 64;
-constexpr int TILE_BYTES = 128 * HD * 2;  // 16384
+constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int Q_BYTES = BQ * HD * 2;    // 16384
+constexpr int KV_BYTES = BKV * HD * 2;  // 8192
+constexpr int KV_STAGES = 3;
 constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + TILE_BYTES;       // 2 stages
-constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;   // 1 stage
-constexpr int OFF_P = OFF_V + TILE_BYTES;       // 128 x 128 bf16 = two 128x64 swizzle atoms
-constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
+constexpr int OFF_K = OFF_Q + Q_BYTES;
+constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
+constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;  // 2 x [128 x 64] bf16 (one swizzle atom column each)
+constexpr int P_BYTES = BQ * BKV * 2;                 // 16384
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
 constexpr int SMEM_TOTAL = 1024 + OFF_BAR + 256;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128;           // O buffers at 128 and 192
-
-// 32 columns of one TMEM lane quadrant -> registers (asynchronous until tmem_ld_wait)
-__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) { ig::tmem_ld32(taddr, v); }
+constexpr int COL_S = 0, COL_O = 128;  // S buffers at 0 / 64, O buffers at 128 / 192
 
 __global__ void __launch_bounds__(THREADS, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int D) {
+attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
+                 __nv_bfloat16* __restrict__ out, int N, int D) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
-  uint64_t* s_full = bars + 7;
-  uint64_t* s_free = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_free = bars + 10;
-  uint64_t* o_full = bars + 11;  // [2]
-  uint64_t* o_free = bars + 13;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [3]
+  uint64_t* v_empty = bars + 10;  // [3]
+  uint64_t* s_full = bars + 13;   // [2]
+  uint64_t* s_free = bars + 15;   // [2]
+  uint64_t* p_full = bars + 17;   // [2]
+  uint64_t* p_free = bars + 19;   // [2]
+  uint64_t* o_full = bars + 21;   // [2]
+  uint64_t* o_free = bars + 23;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -63,20 +67,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
   const int row0 = b * N;  // first token row of this batch element in the qkv matrix
 
   if (warp == 0 && lane == 0) {
-    ig::tma_prefetch_desc(&tm);
+    ig::tma_prefetch_desc(&tmq);
+    ig::tma_prefetch_desc(&tmkv);
     ig::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KV_STAGES; ++s) {
       ig::mbar_init(&k_full[s], 1);
       ig::mbar_init(&k_empty[s], 1);
+      ig::mbar_init(&v_full[s], 1);
+      ig::mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ig::mbar_init(&s_full[s], 1);
+      ig::mbar_init(&s_free[s], 4);
+      ig::mbar_init(&p_full[s], 4);
+      ig::mbar_init(&p_free[s], 1);
       ig::mbar_init(&o_full[s], 1);
       ig::mbar_init(&o_free[s], 4);
     }
-    ig::mbar_init(v_full, 1);
-    ig::mbar_init(v_empty, 1);
-    ig::mbar_init(s_full, 1);
-    ig::mbar_init(s_free, 4);
-    ig::mbar_init(p_full, 4);
-    ig::mbar_init(p_free, 1);
     ig::fence_barrier_init();
   }
   if (warp == 1) {
@@ -91,64 +98,67 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
   if (warp == 0) {
     if (ig::elect_one()) {
       // ===================== TMA producer =====================
-      ig::mbar_expect_tx(q_full, TILE_BYTES);
-      ig::tma_load_2d(smem + OFF_Q, &tm, q_full, h * HD, row0 + q0);
+      ig::mbar_expect_tx(q_full, Q_BYTES);
+      ig::tma_load_2d(smem + OFF_Q, &tmq, q_full, h * HD, row0 + q0);
       for (int j = 0; j < nb; ++j) {
-        const int st = j & 1;
-        ig::mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
-        ig::mbar_expect_tx(&k_full[st], TILE_BYTES);
-        ig::tma_load_2d(smem + OFF_K + st * TILE_BYTES, &tm, &k_full[st], D + h * HD, row0 + j * BKV);
-        ig::mbar_wait(v_empty, (j & 1) ^ 1);
-        ig::mbar_expect_tx(v_full, TILE_BYTES);
-        ig::tma_load_2d(smem + OFF_V, &tm, v_full, 2 * D + h * HD, row0 + j * BKV);
+        const int st = j % KV_STAGES;
+        const uint32_t par = ((j / KV_STAGES) & 1) ^ 1;
+        ig::mbar_wait(&k_empty[st], par);
+        ig::mbar_expect_tx(&k_full[st], KV_BYTES);
+        ig::tma_load_2d(smem + OFF_K + st * KV_BYTES, &tmkv, &k_full[st], D + h * HD, row0 + j * BKV);
+        ig::mbar_wait(&v_empty[st], par);
+        ig::mbar_expect_tx(&v_full[st], KV_BYTES);
+        ig::tma_load_2d(smem + OFF_V + st * KV_BYTES, &tmkv, &v_full[st], 2 * D + h * HD, row0 + j * BKV);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
-    const uint32_t idesc_s = ig::umma_idesc_bf16(BQ, BKV, 0, 0);
-    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);  // B = V, MN-major
+    const uint32_t idesc = ig::umma_idesc_bf16(BQ, BKV, 0, 0);    // S = Q K^T (N = 64 kv)
+    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O = P V  (B = V, MN-major)
     const uint32_t sq = ig::smem_u32(smem + OFF_Q);
-    const uint32_t sp = ig::smem_u32(smem + OFF_P);
+    const uint32_t sk = ig::smem_u32(smem + OFF_K);
     const uint32_t sv = ig::smem_u32(smem + OFF_V);
+    const uint32_t sp = ig::smem_u32(smem + OFF_P);
+    auto issue_qk = [&](int i) {
+      const int st = i % KV_STAGES, sb = i & 1;
+      ig::mbar_wait(&k_full[st], (i / KV_STAGES) & 1);
+      ig::mbar_wait(&s_free[sb], ((i >> 1) & 1) ^ 1);
+      ig::tc_fence_after();
+      if (ig::elect_one()) {
+        const uint64_t dq = ig::umma_desc_sw128(sq, 1024, 16);
+        const uint64_t dk = ig::umma_desc_sw128(sk + st * KV_BYTES, 1024, 16);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ig::umma_bf16(tmem_base + COL_S + sb * BKV, dq + 2 * k, dk + 2 * k, idesc, k > 0);
+        ig::umma_commit(&s_full[sb]);
+        ig::umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
     ig::mbar_wait(q_full, 0);
-    for (int j = 0; j <= nb; ++j) {
-      if (j < nb) {
-        const int st = j & 1;
-        ig::mbar_wait(&k_full[st], (j >> 1) & 1);
-        ig::mbar_wait(s_free, (j & 1) ^ 1);
-        ig::tc_fence_after();
-        if (ig::elect_one()) {
-          const uint64_t dq = ig::umma_desc_sw128(sq, 1024, 16);
-          const uint64_t dk = ig::umma_desc_sw128(ig::smem_u32(smem + OFF_K + st * TILE_BYTES), 1024, 16);
+    issue_qk(0);
+    if (nb > 1) issue_qk(1);
+    for (int j = 0; j < nb; ++j) {
+      const int st = j % KV_STAGES, ob = j & 1;  // O_j = P_j V_j into its own buffer
+      ig::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+      ig::mbar_wait(&p_full[ob], (j >> 1) & 1);
+      ig::mbar_wait(&o_free[ob], ((j >> 1) & 1) ^ 1);
+      ig::tc_fence_after();
+      if (ig::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            ig::umma_bf16(tmem_base + COL_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
-          ig::umma_commit(s_full);
-          ig::umma_commit(&k_empty[st]);
+        for (int k = 0; k < BKV / 16; ++k) {
+          // A = P_j: 128 rows x 64 kv (one swizzle atom column), 32 bytes per K step
+          const uint64_t dp = ig::umma_desc_sw128(sp + ob * P_BYTES + k * 32, 1024, 16);
+          // B = V_j (MN-major): 16 kv rows of 128 bytes per K step, 8-row groups 1024 B apart
+          const uint64_t dv = ig::umma_desc_sw128(sv + st * KV_BYTES + k * 2048, 1024, 1024);
+          ig::umma_bf16(tmem_base + COL_O + ob * HD, dp, dv, idesc_o, k > 0);
         }
-        __syncwarp();
+        ig::umma_commit(&o_full[ob]);
+        ig::umma_commit(&v_empty[st]);
+        ig::umma_commit(&p_free[ob]);
       }
-      if (j > 0) {
-        const int jj = j - 1, ob = jj & 1;  // O_jj = P_jj V_jj into its own buffer
-        ig::mbar_wait(v_full, jj & 1);
-        ig::mbar_wait(p_full, jj & 1);
-        ig::mbar_wait(&o_free[ob], ((jj >> 1) & 1) ^ 1);
-        ig::tc_fence_after();
-        if (ig::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            // A = P: atom (k / 4) of 128 rows x 64 kv, 32 bytes per K step inside the atom
-            const uint64_t dp = ig::umma_desc_sw128(sp + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16);
-            // B = V (MN-major): 16 kv rows of 128 bytes per K step, 8-row groups 1024 B apart
-            const uint64_t dv = ig::umma_desc_sw128(sv + k * 2048, 1024, 1024);
-            ig::umma_bf16(tmem_base + COL_O + ob * HD, dp, dv, idesc_o, k > 0);
-          }
-          ig::umma_commit(&o_full[ob]);
-          ig::umma_commit(v_empty);
-          ig::umma_commit(p_free);
-        }
-        __syncwarp();
-      }
+      __syncwarp();
+      if (j + 2 < nb) issue_qk(j + 2);
     }
   } else {
     // ===================== softmax / output warps (one thread per query row) =====================
@@ -157,7 +167,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + COL_S;
     const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + COL_O;
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-    uint8_t* prow = smem + OFF_P + row * 128;
+    const uint32_t NEG_INF = 0xff800000u;
     float acc[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) acc[i] = 0.f;
@@ -165,79 +175,74 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
     uint32_t va[32], vb[32];
 
     for (int j = 0; j < nb; ++j) {
-      const int kv0 = j * BKV;
-      const bool tail = kv0 + BKV > N;  // block has masked columns
-      ig::mbar_wait(s_full, j & 1);
+      const int kv0 = j * BKV, sb = j & 1;
+      ig::mbar_wait(&s_full[sb], (j >> 1) & 1);
       ig::tc_fence_after();
-      // ---- pass A: row max (next chunk in flight while the current one is reduced)
-      float mb = -INFINITY;
-      ld32(t_s, va);
+      ig::tmem_ld32(t_s + sb * BKV, va);
+      ig::tmem_ld32(t_s + sb * BKV + 32, vb);
       ig::tmem_ld_wait();
+      // the scores are in registers: hand the S buffer back so QK^T of block j+2 can start
+      ig::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ig::mbar_arrive(&s_free[sb]);
+      if (kv0 + BKV > N) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&cur)[32] = (c & 1) ? vb : va;
-        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-        if (c < 3) ld32(t_s + (c + 1) * 32, nxt);
-        else ld32(t_s, nxt);  // first chunk of pass B
-        const int col0 = kv0 + c * 32;
-        if (!tail) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mb = fmaxf(mb, __uint_as_float(cur[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) mb = fmaxf(mb, __uint_as_float(cur[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (kv0 + i >= N) va[i] = NEG_INF;
+          if (kv0 + 32 + i >= N) vb[i] = NEG_INF;
         }
-        ig::tmem_ld_wait();
       }
-      const float m_new = fmaxf(m_ref, mb);
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
+      }
+      const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
       const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 0 on the first block
       const float mc = m_new * sl2;
       m_ref = m_new;
-      l *= alpha;
-      // ---- pass B: exponentials -> P (bf16, swizzled smem); chunk 0 is already in `va`
-      ig::mbar_wait(p_free, (j & 1) ^ 1);
+      // ---- exponentials -> P_j (bf16, swizzled smem)
+      ig::mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
+      uint8_t* prow = smem + OFF_P + sb * P_BYTES + row * 128;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&cur)[32] = (c & 1) ? vb : va;
-        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-        if (c < 3) ld32(t_s + (c + 1) * 32, nxt);
-        const int col0 = kv0 + c * 32;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t(&cur)[32] = c ? vb : va;
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ig::ex2(fmaf(__uint_as_float(cur[2 * i]), sl2, -mc));
-          float p1 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -mc));
-          if (tail) {
-            p0 = (col0 + 2 * i < N) ? p0 : 0.f;
-            p1 = (col0 + 2 * i + 1 < N) ? p1 : 0.f;
-          }
-          l += p0 + p1;
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = ig::ex2(fmaf(__uint_as_float(cur[2 * i]), sl2, -mc));
+          const float p1 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -mc));
+          const float p2 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 2]), sl2, -mc));
+          const float p3 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 3]), sl2, -mc));
+          l0 += p0;
+          l1 += p1;
+          l2 += p2;
+          l3 += p3;
           pk[i] = ig::pack_bf16(p0, p1);
+          pk[i + 1] = ig::pack_bf16(p2, p3);
         }
-        uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;  // 16-byte chunk inside the 128-byte row
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+          const int chunk = c * 4 + q;  // 16-byte chunk inside the 128-byte row
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
-        if (c < 3) ig::tmem_ld_wait();
       }
+      l = fmaf(l, alpha, (l0 + l1) + (l2 + l3));
       ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
-      ig::tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        ig::mbar_arrive(p_full);
-        ig::mbar_arrive(s_free);
-      }
+      if (lane == 0) ig::mbar_arrive(&p_full[sb]);
       // ---- fold the previous block's O into the register accumulators
       if (j > 0) {
         const int jj = j - 1, ob = jj & 1;
         ig::mbar_wait(&o_full[ob], (jj >> 1) & 1);
         ig::tc_fence_after();
-        ld32(t_o + ob * HD, va);
-        ld32(t_o + ob * HD + 32, vb);
+        ig::tmem_ld32(t_o + ob * HD, va);
+        ig::tmem_ld32(t_o + ob * HD + 32, vb);
         ig::tmem_ld_wait();
         ig::tc_fence_before();
         __syncwarp();
@@ -254,8 +259,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restri
       const int jj = nb - 1, ob = jj & 1;
       ig::mbar_wait(&o_full[ob], (jj >> 1) & 1);
       ig::tc_fence_after();
-      ld32(t_o + ob * HD, va);
-      ld32(t_o + ob * HD + 32, vb);
+      ig::tmem_ld32(t_o + ob * HD, va);
+      ig::tmem_ld32(t_o + ob * HD + 32, vb);
       ig::tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -300,11 +305,12 @@ int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t 
                                     attn::SMEM_TOTAL));
     configured = true;
   }
-  CUtensorMap tm;
-  IG_TRY(ig_make_tmap_bf16(&tm, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, 128, 64));
+  CUtensorMap tmq, tmkv;
+  IG_TRY(ig_make_tmap_bf16(&tmq, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BQ, 64));
+  IG_TRY(ig_make_tmap_bf16(&tmkv, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BKV, 64));
   dim3 grid((N + attn::BQ - 1) / attn::BQ, heads, B);
   ig::ProfScope prof(ig::PROF_ATTENTION, st);
-  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_TOTAL, st>>>(tm, static_cast<__nv_bfloat16*>(out), N, D);
+  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_TOTAL, st>>>(tmq, tmkv, static_cast<__nv_bfloat16*>(out), N, D);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }
