@@ -30,6 +30,7 @@ struct PreArgs {
   int n_win, win, T, C, H, W;
   double cm, nodata;
   int has_nodata, cm_is_one;
+  int nodata_i;  // integral nodata value (fast path, constant_multiplier == 1)
   const float* mean;
   const float* std;
   const uint8_t* fmask;
@@ -90,13 +91,20 @@ template <typename RawT> struct RawVal { typedef int type; };
 template <> struct RawVal<float> { typedef float type; };
 template <> struct RawVal<double> { typedef double type; };
 
-template <typename RawT>
+// CB = bands per timestep known at compile time (6 for every InstaGeo config) or 0 = runtime loop.
+// With CB known, the CB band vectors of a timestep are all requested before the first one is
+// consumed: 6 x 16 B in flight per thread instead of one load -> convert -> store chain (which left
+// ~12 KB in flight per SM and the kernel at ~40 % of HBM bandwidth).
+template <typename RawT, int CB>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
   const int groups_per_row = a.win / VEC;
   const int64_t total = static_cast<int64_t>(a.n_win) * a.win * groups_per_row;
-  const int TC = a.T * a.C;
+  const int C = CB ? CB : a.C;
+  const int TC = a.T * C;
   const int gp = a.win / 16;  // tubelet grid side
   const RawT* raw = static_cast<const RawT*>(a.raw);
+  typedef typename RawVal<RawT>::type ValT;
+  constexpr int NB = CB ? CB : 1;  // bands fetched per batch
 
   for (int64_t item = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; item < total;
        item += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -133,51 +141,197 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
 
     uint32_t any_nodata = 0;  // bit i => pixel i is nodata in some band
     for (int t = 0; t < a.T; ++t) {
-      for (int c = 0; c < a.C; ++c) {
-        const int tc = t * a.C + c;
-        const int sb = __ldg(a.band_idx + tc);
-        typename RawVal<RawT>::type v[VEC];
-        load8<RawT>(src0 + sb * a.band_stride, v);
-        const float mean = __ldg(a.mean + c), sd = __ldg(a.std + c);
+      for (int c0 = 0; c0 < C; c0 += NB) {
+        ValT v[NB][VEC];
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) {
+          const int sb = __ldg(a.band_idx + t * C + c0 + cc);
+          load8<RawT>(src0 + sb * a.band_stride, v[cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) {
+          const int c = c0 + cc;
+          const int tc = t * C + c;
+          const float mean = __ldg(a.mean + c), sd = __ldg(a.std + c);
+          float o[VEC];
+          uint32_t m = 0;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            ValT rv = v[cc][i];
+            if (cloud_t[i] & (1u << t)) rv = a.fill_raw;
+            float f;
+            bool nd;
+            if (a.cm_is_one) {  // int16/uint16 -> f32 is exact; float64 -> f32 rounds like PIL mode "F"
+              f = static_cast<float>(rv);
+              nd = static_cast<double>(rv) == a.nodata;
+            } else {
+              const double d = __dmul_rn(static_cast<double>(rv), a.cm);
+              f = __double2float_rn(d);
+              nd = d == a.nodata;
+            }
+            if (a.has_nodata && nd) m |= (1u << i);
+            o[i] = __fdiv_rn(__fsub_rn(f, mean), sd);
+          }
+          any_nodata |= m;
+          if (a.out_f32) {
+            float* dst = a.out_f32 +
+                         (((static_cast<int64_t>(w) * C + c) * a.T + t) * a.win + y) * a.win + x;
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+            __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(o[4], o[5], o[6], o[7]));
+          }
+          if (a.out_patch) {
+            // tubelet row (w, t, y/16, x/16), column c*256 + (y%16)*16 + x%16
+            const int64_t prow = (static_cast<int64_t>(w) * a.T + t) * gp * gp + (y >> 4) * gp + (x >> 4);
+            __nv_bfloat16* dst = a.out_patch + prow * (C * 256) + c * 256 + (y & 15) * 16 + (x & 15);
+            uint4 q;
+            q.x = ig::pack_bf16(o[0], o[1]);
+            q.y = ig::pack_bf16(o[2], o[3]);
+            q.z = ig::pack_bf16(o[4], o[5]);
+            q.w = ig::pack_bf16(o[6], o[7]);
+            *reinterpret_cast<uint4*>(dst) = q;
+          }
+          if (a.mask_elem) {
+            uint8_t* dst = a.mask_elem + ((static_cast<int64_t>(w) * TC + tc) * a.win + y) * a.win + x;
+            uint2 q;
+            q.x = ((m >> 0) & 1u) | (((m >> 1) & 1u) << 8) | (((m >> 2) & 1u) << 16) | (((m >> 3) & 1u) << 24);
+            q.y = ((m >> 4) & 1u) | (((m >> 5) & 1u) << 8) | (((m >> 6) & 1u) << 16) | (((m >> 7) & 1u) << 24);
+            __stcs(reinterpret_cast<uint2*>(dst), q);
+          }
+        }
+      }
+    }
+    if (a.mask_px) {
+      uint8_t* dst = a.mask_px + (static_cast<int64_t>(w) * a.win + y) * a.win + x;
+      const uint32_t m = any_nodata;
+      uint2 q;
+      q.x = ((m >> 0) & 1u) | (((m >> 1) & 1u) << 8) | (((m >> 2) & 1u) << 16) | (((m >> 3) & 1u) << 24);
+      q.y = ((m >> 4) & 1u) | (((m >> 5) & 1u) << 8) | (((m >> 6) & 1u) << 16) | (((m >> 7) & 1u) << 24);
+      *reinterpret_cast<uint2*>(dst) = q;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path: int16 / uint16 rasters, 6 bands per timestep, no Fmask (every BASELINE config).
+// Same arithmetic as the generic kernel, restated to cost ~3x fewer issue slots and registers:
+//   * the 6 band vectors of a timestep stay PACKED (6 x uint4 = 24 registers) and are all requested
+//     before the first is consumed -> 96 B in flight per thread at 4 CTAs/SM (64 registers);
+//   * nodata compare in the integer domain when constant_multiplier == 1 (exactly equivalent:
+//     int16 -> f64 is exact, so f64(raw) == nodata  <=>  raw == nodata for integral nodata);
+//   * (f - mean) / std by Markstein's FMA sequence on a once-per-band correctly rounded reciprocal:
+//     q = a*y; r = fma(-b,q,a); q = fma(r,y,q); r = fma(-b,q,a); q = fma(r,y,q)  is the correctly
+//     rounded quotient (no over/underflow, divisor significand not all ones -- otherwise the
+//     IEEE division instruction sequence is used).  tests/test_gpu_preprocess.py checks it against
+//     true division for all 65536 raw values.
+struct DivC {
+  float b, y;
+  bool safe;
+};
+__device__ __forceinline__ DivC make_div(float b) {
+  DivC d;
+  d.b = b;
+  d.y = __frcp_rn(b);
+  const uint32_t u = __float_as_uint(b);
+  const uint32_t e = (u >> 23) & 0xffu;
+  d.safe = (e > 67u) && (e < 187u) && ((u & 0x7fffffu) != 0x7fffffu);  // 2^-60 < |b| < 2^60
+  return d;
+}
+__device__ __forceinline__ float div_by(float a, const DivC& d) {
+  if (!d.safe) return __fdiv_rn(a, d.b);
+  float q = __fmul_rn(a, d.y);
+  float r = __fmaf_rn(-d.b, q, a);
+  q = __fmaf_rn(r, d.y, q);
+  r = __fmaf_rn(-d.b, q, a);
+  return __fmaf_rn(r, d.y, q);
+}
+
+template <typename RawT>
+__device__ __forceinline__ uint4 load_raw8(const RawT* p) {
+  const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+  if ((ad & 15) == 0) return __ldg(reinterpret_cast<const uint4*>(p));
+  uint4 q;
+  if ((ad & 7) == 0) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p)), b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
+    q = make_uint4(a.x, a.y, b.x, b.y);
+  } else if ((ad & 3) == 0) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    q = make_uint4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(w + 3));
+  } else {
+    const unsigned short* h = reinterpret_cast<const unsigned short*>(p);
+    q.x = __ldg(h) | (static_cast<uint32_t>(__ldg(h + 1)) << 16);
+    q.y = __ldg(h + 2) | (static_cast<uint32_t>(__ldg(h + 3)) << 16);
+    q.z = __ldg(h + 4) | (static_cast<uint32_t>(__ldg(h + 5)) << 16);
+    q.w = __ldg(h + 6) | (static_cast<uint32_t>(__ldg(h + 7)) << 16);
+  }
+  return q;
+}
+template <typename RawT>
+__device__ __forceinline__ int raw_at(const uint4& q, int i) {
+  const uint32_t w = (i < 2) ? q.x : (i < 4) ? q.y : (i < 6) ? q.z : q.w;
+  const uint32_t h = (i & 1) ? (w >> 16) : (w & 0xffffu);
+  return static_cast<int>(static_cast<RawT>(h));
+}
+
+template <typename RawT, bool CM1>
+__global__ void __launch_bounds__(256, 4) preprocess_i16x6_kernel(const PreArgs a) {
+  constexpr int C = 6;
+  const int groups_per_row = a.win / VEC;
+  const int64_t total = static_cast<int64_t>(a.n_win) * a.win * groups_per_row;
+  const int gp = a.win / 16;
+  const RawT* raw = static_cast<const RawT*>(a.raw);
+  for (int64_t item = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; item < total;
+       item += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(item % groups_per_row);
+    const int64_t r = item / groups_per_row;
+    const int y = static_cast<int>(r % a.win);
+    const int w = static_cast<int>(r / a.win);
+    int img = w, top = 0, left = 0;
+    if (a.win_yx) {
+      img = __ldg(a.win_yx + 3 * w);
+      top = __ldg(a.win_yx + 3 * w + 1);
+      left = __ldg(a.win_yx + 3 * w + 2);
+    }
+    const int x = g * VEC;
+    const RawT* src0 = raw + img * a.img_stride + (top + y) * a.row_stride + (left + x);
+    uint32_t any_nodata = 0;
+    for (int t = 0; t < a.T; ++t) {
+      uint4 rv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) rv[c] = load_raw8<RawT>(src0 + __ldg(a.band_idx + t * C + c) * a.band_stride);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float mean = __ldg(a.mean + c);
+        const DivC dv = make_div(__ldg(a.std + c));
         float o[VEC];
         uint32_t m = 0;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          typename RawVal<RawT>::type rv = v[i];
-          if (cloud_t[i] & (1u << t)) rv = a.fill_raw;
+          const int rr = raw_at<RawT>(rv[c], i);
           float f;
-          bool nd;
-          if (a.cm_is_one) {  // int16/uint16 -> f32 is exact; float64 -> f32 rounds like PIL mode "F"
-            f = static_cast<float>(rv);
-            nd = static_cast<double>(rv) == a.nodata;
+          if (CM1) {
+            f = static_cast<float>(rr);
+            if (a.has_nodata && rr == a.nodata_i) m |= (1u << i);
           } else {
-            const double d = __dmul_rn(static_cast<double>(rv), a.cm);
+            const double d = __dmul_rn(static_cast<double>(rr), a.cm);
             f = __double2float_rn(d);
-            nd = d == a.nodata;
+            if (a.has_nodata && d == a.nodata) m |= (1u << i);
           }
-          if (a.has_nodata && nd) m |= (1u << i);
-          o[i] = __fdiv_rn(__fsub_rn(f, mean), sd);
+          o[i] = div_by(__fsub_rn(f, mean), dv);
         }
         any_nodata |= m;
         if (a.out_f32) {
-          float* dst = a.out_f32 +
-                       (((static_cast<int64_t>(w) * a.C + c) * a.T + t) * a.win + y) * a.win + x;
+          float* dst = a.out_f32 + (((static_cast<int64_t>(w) * C + c) * a.T + t) * a.win + y) * a.win + x;
           __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
           __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(o[4], o[5], o[6], o[7]));
         }
         if (a.out_patch) {
-          // tubelet row (w, t, y/16, x/16), column c*256 + (y%16)*16 + x%16
           const int64_t prow = (static_cast<int64_t>(w) * a.T + t) * gp * gp + (y >> 4) * gp + (x >> 4);
-          __nv_bfloat16* dst = a.out_patch + prow * (a.C * 256) + c * 256 + (y & 15) * 16 + (x & 15);
-          uint4 q;
-          q.x = ig::pack_bf16(o[0], o[1]);
-          q.y = ig::pack_bf16(o[2], o[3]);
-          q.z = ig::pack_bf16(o[4], o[5]);
-          q.w = ig::pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(dst) = q;
+          __nv_bfloat16* dst = a.out_patch + prow * (C * 256) + c * 256 + (y & 15) * 16 + (x & 15);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(ig::pack_bf16(o[0], o[1]), ig::pack_bf16(o[2], o[3]),
+                                                      ig::pack_bf16(o[4], o[5]), ig::pack_bf16(o[6], o[7]));
         }
         if (a.mask_elem) {
-          uint8_t* dst = a.mask_elem + ((static_cast<int64_t>(w) * TC + tc) * a.win + y) * a.win + x;
+          uint8_t* dst = a.mask_elem + ((static_cast<int64_t>(w) * (a.T * C) + t * C + c) * a.win + y) * a.win + x;
           uint2 q;
           q.x = ((m >> 0) & 1u) | (((m >> 1) & 1u) << 8) | (((m >> 2) & 1u) << 16) | (((m >> 3) & 1u) << 24);
           q.y = ((m >> 4) & 1u) | (((m >> 5) & 1u) << 8) | (((m >> 6) & 1u) << 16) | (((m >> 7) & 1u) << 24);
@@ -194,6 +348,20 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
       *reinterpret_cast<uint2*>(dst) = q;
     }
   }
+}
+
+template <typename RawT>
+void launch_pre(const PreArgs& a, unsigned blocks, int threads, cudaStream_t st) {
+  preprocess_kernel<RawT, 0><<<blocks, threads, 0, st>>>(a);
+}
+template <typename RawT>
+void launch_pre_i16(const PreArgs& a, unsigned blocks, int threads, cudaStream_t st) {
+  const bool fast = a.C == 6 && a.fmask == nullptr && (a.cm_is_one || (fabs(a.cm) > 1e-12 && fabs(a.cm) < 1e12));
+  if (!fast) return launch_pre<RawT>(a, blocks, threads, st);
+  if (a.cm_is_one)
+    preprocess_i16x6_kernel<RawT, true><<<blocks, threads, 0, st>>>(a);
+  else
+    preprocess_i16x6_kernel<RawT, false><<<blocks, threads, 0, st>>>(a);
 }
 
 }  // namespace
@@ -241,6 +409,7 @@ extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_sr
   a.nodata = no_data_value;
   a.has_nodata = has_nodata;
   a.cm_is_one = constant_multiplier == 1.0;
+  a.nodata_i = 0;
   a.mean = mean;
   a.std = std;
   a.fmask = fmask_bits ? fmask : nullptr;
@@ -259,14 +428,22 @@ extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_sr
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ig::ProfScope prof(ig::PROF_PREPROCESS, st);
-  if (raw_dtype == IG_I16)
-    preprocess_kernel<int16_t><<<static_cast<unsigned>(blocks), threads, 0, st>>>(a);
-  else if (raw_dtype == IG_U16)
-    preprocess_kernel<uint16_t><<<static_cast<unsigned>(blocks), threads, 0, st>>>(a);
-  else if (raw_dtype == IG_F32)
-    preprocess_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, st>>>(a);
+  if (raw_dtype == IG_I16 || raw_dtype == IG_U16) {
+    // integer-domain nodata compare of the fast path: a non-integral (or out-of-range) nodata value can
+    // never equal an int16/uint16 sample, so with constant_multiplier == 1 the mask is simply empty
+    PreArgs f = a;
+    if (f.cm_is_one && f.has_nodata) {
+      if (no_data_value == floor(no_data_value) && fabs(no_data_value) < 1e9) f.nodata_i = static_cast<int>(no_data_value);
+      else f.has_nodata = 0;
+    }
+    // (the generic kernel keeps the float64 compare, so only hand it the adjusted args on the fast path)
+    const bool fastable = f.C == 6 && f.fmask == nullptr;
+    if (raw_dtype == IG_I16) launch_pre_i16<int16_t>(fastable ? f : a, static_cast<unsigned>(blocks), threads, st);
+    else launch_pre_i16<uint16_t>(fastable ? f : a, static_cast<unsigned>(blocks), threads, st);
+  } else if (raw_dtype == IG_F32)
+    launch_pre<float>(a, static_cast<unsigned>(blocks), threads, st);
   else
-    preprocess_kernel<double><<<static_cast<unsigned>(blocks), threads, 0, st>>>(a);
+    launch_pre<double>(a, static_cast<unsigned>(blocks), threads, st);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }

@@ -124,3 +124,31 @@ def test_edge_cases(cuda_dev):
     o = ops.preprocess(raw, ops.PreprocessSpec(FLOOD_MEAN, FLOOD_STD, 1, None, 1e-4, None, cuda_dev), win=16)["f32"]
     want = OP.normalize(raw[0].cpu().numpy() * 1e-4, FLOOD_MEAN, FLOOD_STD, 1)
     assert np.array_equal(o[0].cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.int16, np.uint16])
+@pytest.mark.parametrize("cm", [1.0, 1e-4])
+def test_every_raw_value_divides_exactly(cuda_dev, dtype, cm):
+    """The fast path replaces the IEEE division by an FMA sequence on a precomputed reciprocal:
+    check all 65536 raw values x 6 bands against the oracle's true division, for the two config
+    statistics and for adversarial divisors (tiny, huge, near powers of two, all-ones significand)."""
+    from instageo_b200 import ops
+    vals = np.arange(65536, dtype=np.uint16).view(dtype).reshape(256, 256)
+    raw = np.broadcast_to(vals, (1, 6, 256, 256)).copy()
+    rng = np.random.default_rng(5)
+    stat_sets = [(FLOOD_MEAN, FLOOD_STD), (CROP_MEAN, CROP_STD)]
+    for _ in range(3):
+        stat_sets.append((list(rng.uniform(-3000, 3000, 6)), list(np.exp(rng.uniform(-9, 9, 6)))))
+    ones = float(np.frombuffer(np.uint32(0x3fffffff).tobytes(), dtype=np.float32)[0])  # 1.9999999
+    stat_sets.append(([0.0, 1.0, -1.0, 0.5, 1e-3, 123.456], [1.0, ones, 3.0, 1.0000001, 0.99999994, 7.0]))
+    stat_sets.append(([0.0, 1e-20, 5.0, -7.0, 0.25, 1e3], [1e-25, 1e25, 3e-19, 2e18, 1.5e-18, 0.1]))  # outside the FMA path's safe range
+    for mean, std in stat_sets:
+        spec = ops.PreprocessSpec(mean, std, 1, None, cm, -9999, cuda_dev)
+        torch_raw = torch.from_numpy(raw.view(np.int16)).to(cuda_dev)
+        if dtype == np.uint16:
+            torch_raw = torch_raw.view(torch.uint16)
+        out = ops.preprocess(torch_raw, spec, win=256, want_f32=True, want_mask_elem=True)
+        want, mask = OP.preprocess_chip(raw[0], None, cm, mean, std, 1, -9999)
+        assert np.array_equal(out["f32"][0].cpu().numpy(), want), (mean, std)
+        assert np.array_equal(out["mask_elem"][0].cpu().numpy(), mask)

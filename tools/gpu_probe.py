@@ -148,15 +148,27 @@ def probe_stitch():
         h_ref = [int((cls == k).sum()) for k in range(nc)] + [int((cls == -1).sum())]
         print(f"[stitch {H}x{W} win{win} s{stride} nc{nc}] avg bit-exact={a_eq} cls={c_eq} hist={list(hist)==h_ref}")
         RES[f"stitch_{H}_{stride}_{nc}"] = dict(avg=a_eq, cls=c_eq, hist=list(map(int, hist)) == h_ref)
-    H = W = 3660; win = 224; nc = 2
-    for stride in (224, 112):
-        ys = ops.window_origins(H, win, stride, True); xs = ops.window_origins(W, win, stride, True)
-        lg = torch.randn(len(ys) * len(xs), nc, win, win, device=dev)
-        ms = timeit(lambda: ops.stitch(lg, ys, xs, H, W), iters=5)
-        by = lg.numel() * 4 + H * W
-        print(f"[stitch perf stride {stride}] {ms:.3f} ms {by/ms/1e6:.1f} GB/s")
-        RES[f"stitch_gbs_{stride}"] = by / ms / 1e6
-
+    from instageo_b200 import _lib
+    H = W = 3660; win = 224
+    for nc in (2, 13):
+        for stride in (224, 112):
+            ys = ops.window_origins(H, win, stride, True); xs = ops.window_origins(W, win, stride, True)
+            lg = torch.randn(len(ys) * len(xs), nc, win, win, device=dev)
+            nd = torch.zeros(H, W, dtype=torch.bool, device=dev)
+            for _ in range(3):
+                ops.stitch(lg, ys, xs, H, W, nodata_px=nd)
+            torch.cuda.synchronize()
+            _lib.profile_enable(True); _lib.profile_report()
+            for _ in range(10):
+                ops.stitch(lg, ys, xs, H, W, nodata_px=nd)
+            torch.cuda.synchronize()
+            ms, n = _lib.profile_report()["stitch"]
+            _lib.profile_enable(False)
+            ms /= n
+            by = lg.numel() * 4 + 2 * H * W
+            print(f"[stitch perf nc{nc} stride {stride}] kernel {ms*1e3:.1f} us  {by/ms/1e6:.1f} GB/s ({by/1e6:.0f} MB)")
+            RES[f"stitch_gbs_nc{nc}_{stride}"] = by / ms / 1e6
+            del lg
 
 def probe_model():
     from instageo_b200.model import PrithviSeg
