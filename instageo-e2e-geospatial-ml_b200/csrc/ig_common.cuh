@@ -43,6 +43,11 @@ int ig_num_sms();
 int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_pitch, uint32_t box_rows, uint32_t box_cols);
 
+// General tiled TMA descriptor (no swizzle, zero fill out of bounds): dims/box innermost first,
+// strides_bytes[i] = byte stride of dimension i+1.  dtype = IG_F32 | IG_BF16 | IG_I16 | IG_U16.
+int ig_make_tmap_nd(CUtensorMap* map, int dtype, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
+
 // Optional per-launch CUDA-event timing (ig_profile_enable): brackets a launch with two events on
 // the launching stream; ig_profile_report sums elapsed time per kernel family.
 namespace ig {
@@ -152,6 +157,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

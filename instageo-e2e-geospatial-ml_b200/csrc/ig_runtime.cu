@@ -87,6 +87,40 @@ int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return IG_OK;
 }
 
+int ig_make_tmap_nd(CUtensorMap* map, int dtype, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  IG_REQUIRE(enc != nullptr, IG_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  IG_REQUIRE(rank >= 1 && rank <= 5, IG_EINVAL, "TMA rank %d unsupported", rank);
+  IG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IG_EINVAL, "TMA base %p not 16-byte aligned", base);
+  CUtensorMapDataType dt;
+  switch (dtype) {
+    case IG_F32: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    case IG_BF16: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+    case IG_I16: case IG_U16: dt = CU_TENSOR_MAP_DATA_TYPE_UINT16; break;
+    default: ig_set_error("TMA dtype %d unsupported", dtype); return IG_EINVAL;
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    IG_REQUIRE(box[i] >= 1 && box[i] <= 256, IG_ESHAPE, "TMA box dim %d = %u unsupported", i, box[i]);
+    if (i > 0) {
+      st[i - 1] = strides_bytes[i - 1];
+      IG_REQUIRE(strides_bytes[i - 1] % 16 == 0, IG_ESHAPE, "TMA stride %d = %llu bytes not a multiple of 16", i,
+                 static_cast<unsigned long long>(strides_bytes[i - 1]));
+    }
+  }
+  const CUresult r = enc(map, dt, rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);  // out-of-bounds elements read as zero
+  IG_REQUIRE(r == CUDA_SUCCESS, IG_ECUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank,
+             static_cast<int>(r));
+  return IG_OK;
+}
+
 // ----------------------------------------------------------------------------- launch profiling
 namespace {
 struct ProfRec { int cat; cudaEvent_t e0, e1; };
