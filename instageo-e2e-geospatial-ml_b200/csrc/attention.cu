@@ -7,21 +7,21 @@
 // matrix.  Output is written as [B*N, D] (head-major), the exact operand of the proj GEMM.
 //
 // One CTA = 128 query rows of one (batch, head); 2 CTAs per SM.  tcgen05 throughout:
-//   S_j = Q K_j^T : UMMA 128x64x16, both operands K-major (128-byte swizzle), S double-buffered in TMEM
-//   O_j = P_j V_j : UMMA 128x64x16, A = P_j (bf16, written to swizzled smem by the softmax warps),
-//                   B = V_j used MN-major straight from its [kv, 64] tile (no transpose pass);
-//                   NOT accumulated in TMEM: each block's product lands in its own TMEM buffer
-// KV blocks are 64 wide so that two S tiles and two O tiles fit the CTA's 256 TMEM columns: the
-// tensor core computes S_{j+1}/S_{j+2} while the softmax warps work on S_j, and they never wait for it.
-// Softmax (4 warps, thread <-> TMEM lane <-> query row): single pass with a running max.  Per block the
-// 64 scores of the row are pulled into registers once (the S buffer is released immediately), reduced
-// to the new max, exponentiated against it (masked columns are -inf -> 0), written as P_j; then the
-// PREVIOUS block's O_{j-1} is folded into register accumulators:
-//   acc = acc * exp(m_{j-2} - m_{j-1}) + O_{j-1}.
-// Keeping the running output in registers means no TMEM read-modify-write rescale and no ordering
-// hazard between a rescale and the next P V MMA: the tensor core only ever writes fresh tiles.
-// Max / sum reductions use 4 independent chains (a single dependent FADD/FMNMX chain per row cost as
-// much as the exponentials).  The exp count (N^2 per head) on the 16-lane/clk MUFU is the floor.
+//   S_j  = Q K_j^T  : UMMA 128x64x16, both operands K-major (128-byte swizzle), S double-buffered in TMEM
+//   O   += P_j V_j  : UMMA 128x64x16, A = P_j (bf16, written to swizzled smem by the softmax warps),
+//                     B = V_j used MN-major straight from its [kv, 64] tile (no transpose pass)
+//   L   += P_j 1    : UMMA 128x8x16 against a tile of ones: the softmax denominator is accumulated by the
+//                     tensor core from the SAME bf16-rounded probabilities as the numerator
+// O and L stay in TMEM for the whole KV loop.  The softmax warps (thread <-> TMEM lane <-> query row)
+// therefore do nothing per block but: pull the 64 scores, take their max, exponentiate against a
+// reference max, and write P_j.  The reference max is LAZY: it is only raised when a block's max exceeds
+// it by more than 2^8 in the exp2 domain (probabilities stay <= 256, harmless in f32/bf16), and only then
+// is O/L rescaled in TMEM (tcgen05.ld -> multiply -> tcgen05.st, between PV_{j-1} and PV_j).  With
+// attention logits of trained or random-init ViTs that happens in the first block or two; every other
+// block costs 1 FFMA + 1 MUFU + 1/3 FMNMX3 + 1/2 F2F per score.  The first version folded every block's
+// O into 64 register accumulators (64 FFMA + 64 FADD per row and block on top of the exponentials) and ran
+// at 45 % issue utilisation, 2.9x above the MUFU floor (profiles/r01_ncu_attention_before.txt).
+// In the last KV block only the 16-column groups that contain valid keys are exponentiated.
 #include "ig_ops.cuh"
 
 namespace attn {
@@ -35,11 +35,14 @@ constexpr int OFF_K = OFF_Q + Q_BYTES;
 constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
 constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;  // 2 x [128 x 64] bf16 (one swizzle atom column each)
 constexpr int P_BYTES = BQ * BKV * 2;                 // 16384
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+constexpr int OFF_ONES = OFF_P + 2 * P_BYTES;         // [8 x 64] bf16 ones (K-major B operand of the L MMA)
+constexpr int OFF_BAR = OFF_ONES + 1024;
 constexpr int SMEM_TOTAL = 1024 + OFF_BAR + 256;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128;  // S buffers at 0 / 64, O buffers at 128 / 192
+constexpr int COL_S = 0, COL_O = 128, COL_L = 192;  // S buffers at 0 / 64, O at 128..191, L at 192..199
+constexpr float RESCALE_LOG2 = 8.f;                 // raise the reference max only for jumps > 2^8
+static_assert(OFF_ONES % 1024 == 0, "UMMA operand tiles are 1024-byte aligned");
 
 __global__ void __launch_bounds__(THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
@@ -57,9 +60,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   uint64_t* s_free = bars + 15;   // [2]
   uint64_t* p_full = bars + 17;   // [2]
   uint64_t* p_free = bars + 19;   // [2]
-  uint64_t* o_full = bars + 21;   // [2]
-  uint64_t* o_free = bars + 23;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* o_done = bars + 21;   // [2]  PV_j (and everything before it) has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -81,14 +83,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       ig::mbar_init(&s_free[s], 4);
       ig::mbar_init(&p_full[s], 4);
       ig::mbar_init(&p_free[s], 1);
-      ig::mbar_init(&o_full[s], 1);
-      ig::mbar_init(&o_free[s], 4);
+      ig::mbar_init(&o_done[s], 1);
     }
     ig::fence_barrier_init();
   }
   if (warp == 1) {
     ig::tmem_alloc(tmem_ptr, TMEM_COLS);
     ig::tmem_relinquish();
+  }
+  if (warp >= 2) {  // the ones tile (bf16 1.0 everywhere: the swizzle does not matter)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + OFF_ONES);
+    for (int i = threadIdx.x - 64; i < 256; i += THREADS - 64) ones[i] = 0x3f803f80u;
+    ig::fence_proxy_async_smem();
   }
   ig::tc_fence_before();
   __syncthreads();
@@ -114,11 +120,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
     const uint32_t idesc = ig::umma_idesc_bf16(BQ, BKV, 0, 0);    // S = Q K^T (N = 64 kv)
-    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O = P V  (B = V, MN-major)
+    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O += P V  (B = V, MN-major)
+    const uint32_t idesc_l = ig::umma_idesc_bf16(BQ, 8, 0, 0);    // L += P 1  (B = ones, K-major, N = 8)
     const uint32_t sq = ig::smem_u32(smem + OFF_Q);
     const uint32_t sk = ig::smem_u32(smem + OFF_K);
     const uint32_t sv = ig::smem_u32(smem + OFF_V);
     const uint32_t sp = ig::smem_u32(smem + OFF_P);
+    const uint32_t so = ig::smem_u32(smem + OFF_ONES);
     auto issue_qk = [&](int i) {
       const int st = i % KV_STAGES, sb = i & 1;
       ig::mbar_wait(&k_full[st], (i / KV_STAGES) & 1);
@@ -139,23 +147,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     issue_qk(0);
     if (nb > 1) issue_qk(1);
     for (int j = 0; j < nb; ++j) {
-      const int st = j % KV_STAGES, ob = j & 1;  // O_j = P_j V_j into its own buffer
+      const int st = j % KV_STAGES, pb = j & 1;
       ig::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-      ig::mbar_wait(&p_full[ob], (j >> 1) & 1);
-      ig::mbar_wait(&o_free[ob], ((j >> 1) & 1) ^ 1);
+      ig::mbar_wait(&p_full[pb], (j >> 1) & 1);  // P_j is in smem and any rescale of O / L is finished
       ig::tc_fence_after();
       if (ig::elect_one()) {
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           // A = P_j: 128 rows x 64 kv (one swizzle atom column), 32 bytes per K step
-          const uint64_t dp = ig::umma_desc_sw128(sp + ob * P_BYTES + k * 32, 1024, 16);
+          const uint64_t dp = ig::umma_desc_sw128(sp + pb * P_BYTES + k * 32, 1024, 16);
           // B = V_j (MN-major): 16 kv rows of 128 bytes per K step, 8-row groups 1024 B apart
           const uint64_t dv = ig::umma_desc_sw128(sv + st * KV_BYTES + k * 2048, 1024, 1024);
-          ig::umma_bf16(tmem_base + COL_O + ob * HD, dp, dv, idesc_o, k > 0);
+          ig::umma_bf16(tmem_base + COL_O, dp, dv, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          const uint64_t d1 = ig::umma_desc_sw128(so + k * 32, 1024, 16);
+          ig::umma_bf16(tmem_base + COL_L, dp, d1, idesc_l, (j > 0 || k > 0) ? 1u : 0u);
         }
-        ig::umma_commit(&o_full[ob]);
+        ig::umma_commit(&o_done[pb]);
         ig::umma_commit(&v_empty[st]);
-        ig::umma_commit(&p_free[ob]);
+        ig::umma_commit(&p_free[pb]);
       }
       __syncwarp();
       if (j + 2 < nb) issue_qk(j + 2);
@@ -164,121 +173,117 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     // ===================== softmax / output warps (one thread per query row) =====================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + COL_S;
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + COL_O;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t t_s = t_lane + COL_S, t_o = t_lane + COL_O, t_l = t_lane + COL_L;
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+    const float jump = RESCALE_LOG2 / sl2;           // the same threshold in raw score units
     const uint32_t NEG_INF = 0xff800000u;
-    float acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
-    float m_ref = -INFINITY, l = 0.f, alpha_pend = 0.f;
-    uint32_t va[32], vb[32];
+    float m_ref = -INFINITY;
+    uint32_t sc[64];
+    uint32_t(&sa)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc);
+    uint32_t(&sb2)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc + 32);
 
     for (int j = 0; j < nb; ++j) {
       const int kv0 = j * BKV, sb = j & 1;
+      const int nvalid = min(BKV, N - kv0);  // warp-uniform
       ig::mbar_wait(&s_full[sb], (j >> 1) & 1);
       ig::tc_fence_after();
-      ig::tmem_ld32(t_s + sb * BKV, va);
-      ig::tmem_ld32(t_s + sb * BKV + 32, vb);
+      ig::tmem_ld32(t_s + sb * BKV, sa);
+      ig::tmem_ld32(t_s + sb * BKV + 32, sb2);
       ig::tmem_ld_wait();
       // the scores are in registers: hand the S buffer back so QK^T of block j+2 can start
       ig::tc_fence_before();
       __syncwarp();
       if (lane == 0) ig::mbar_arrive(&s_free[sb]);
-      if (kv0 + BKV > N) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
+      if (nvalid < BKV) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (kv0 + i >= N) va[i] = NEG_INF;
-          if (kv0 + 32 + i >= N) vb[i] = NEG_INF;
-        }
+        for (int i = 0; i < 64; ++i)
+          if (i >= nvalid) sc[i] = NEG_INF;
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
-        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
-        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
+      for (int i = 0; i < 64; i += 8) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sc[i + 4]), __uint_as_float(sc[i + 5])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sc[i + 6]), __uint_as_float(sc[i + 7])));
       }
-      const float m_new = fmaxf(fmaxf(m_ref, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
-      const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 0 on the first block
-      const float mc = m_new * sl2;
-      m_ref = m_new;
-      // ---- exponentials -> P_j (bf16, swizzled smem)
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (j == 0) {
+        m_ref = m_blk;
+      } else {
+        const bool need = m_blk > m_ref + jump;
+        if (__any_sync(0xffffffffu, need)) {
+          // ---- lazy rescale: O and L of this warp's 32 rows are multiplied by 2^(old - new) in TMEM.
+          // PV_{j-1} must have completed; PV_j cannot start before this warp arrives on p_full below.
+          const float m_new = need ? m_blk : m_ref;
+          const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 1 for rows that keep their reference
+          m_ref = m_new;
+          ig::mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          ig::tc_fence_after();
+          uint32_t t[32];
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            ig::tmem_ld32(t_o + c, t);
+            ig::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            ig::tmem_st32(t_o + c, t);
+          }
+          const uint32_t lv = ig::tmem_ld1(t_l);
+          ig::tmem_ld_wait();
+          ig::tmem_st1(t_l, __float_as_uint(__uint_as_float(lv) * alpha));
+          ig::tmem_st_wait();
+        }
+      }
+      const float mc = m_ref * sl2;
+      // ---- exponentials -> P_j (bf16, swizzled smem); fully masked 16-column groups are written as zeros
       ig::mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
       uint8_t* prow = smem + OFF_P + sb * P_BYTES + row * 128;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t(&cur)[32] = c ? vb : va;
-        uint32_t pk[16];
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[8];
+        if (g * 16 < nvalid) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ig::ex2(fmaf(__uint_as_float(cur[2 * i]), sl2, -mc));
-          const float p1 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -mc));
-          const float p2 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 2]), sl2, -mc));
-          const float p3 = ig::ex2(fmaf(__uint_as_float(cur[2 * i + 3]), sl2, -mc));
-          l0 += p0;
-          l1 += p1;
-          l2 += p2;
-          l3 += p3;
-          pk[i] = ig::pack_bf16(p0, p1);
-          pk[i + 1] = ig::pack_bf16(p2, p3);
+          for (int i = 0; i < 8; ++i) {
+            const float p0 = ig::ex2(fmaf(__uint_as_float(sc[g * 16 + 2 * i]), sl2, -mc));
+            const float p1 = ig::ex2(fmaf(__uint_as_float(sc[g * 16 + 2 * i + 1]), sl2, -mc));
+            pk[i] = ig::pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = 0u;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = c * 4 + q;  // 16-byte chunk inside the 128-byte row
+        for (int q = 0; q < 2; ++q) {
+          const int chunk = g * 2 + q;  // 16-byte chunk inside the 128-byte row
           *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
-      l = fmaf(l, alpha, (l0 + l1) + (l2 + l3));
       ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
+      ig::tc_fence_before();         // orders a rescale's tcgen05.st before the MMA warp's PV_j
       __syncwarp();
       if (lane == 0) ig::mbar_arrive(&p_full[sb]);
-      // ---- fold the previous block's O into the register accumulators
-      if (j > 0) {
-        const int jj = j - 1, ob = jj & 1;
-        ig::mbar_wait(&o_full[ob], (jj >> 1) & 1);
-        ig::tc_fence_after();
-        ig::tmem_ld32(t_o + ob * HD, va);
-        ig::tmem_ld32(t_o + ob * HD + 32, vb);
-        ig::tmem_ld_wait();
-        ig::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ig::mbar_arrive(&o_free[ob]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          acc[i] = fmaf(acc[i], alpha_pend, __uint_as_float(va[i]));
-          acc[32 + i] = fmaf(acc[32 + i], alpha_pend, __uint_as_float(vb[i]));
-        }
-      }
-      alpha_pend = alpha;
     }
-    {
-      const int jj = nb - 1, ob = jj & 1;
-      ig::mbar_wait(&o_full[ob], (jj >> 1) & 1);
-      ig::tc_fence_after();
-      ig::tmem_ld32(t_o + ob * HD, va);
-      ig::tmem_ld32(t_o + ob * HD + 32, vb);
-      ig::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = fmaf(acc[i], alpha_pend, __uint_as_float(va[i]));
-        acc[32 + i] = fmaf(acc[32 + i], alpha_pend, __uint_as_float(vb[i]));
-      }
-    }
-    const float inv = 1.f / l;
+    // ---- epilogue: O / L
+    ig::mbar_wait(&o_done[(nb - 1) & 1], ((nb - 1) >> 1) & 1);
+    ig::tc_fence_after();
+    ig::tmem_ld32(t_o, sa);
+    ig::tmem_ld32(t_o + 32, sb2);
+    const uint32_t lv = ig::tmem_ld1(t_l);
+    ig::tmem_ld_wait();
+    const float inv = 1.f / __uint_as_float(lv);
     const int qrow = q0 + row;
     if (qrow < N) {
       __nv_bfloat16* orow = out + (static_cast<int64_t>(row0) + qrow) * D + h * HD;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         uint4 o;
-        o.x = ig::pack_bf16(acc[8 * q + 0] * inv, acc[8 * q + 1] * inv);
-        o.y = ig::pack_bf16(acc[8 * q + 2] * inv, acc[8 * q + 3] * inv);
-        o.z = ig::pack_bf16(acc[8 * q + 4] * inv, acc[8 * q + 5] * inv);
-        o.w = ig::pack_bf16(acc[8 * q + 6] * inv, acc[8 * q + 7] * inv);
+        o.x = ig::pack_bf16(__uint_as_float(sc[8 * q + 0]) * inv, __uint_as_float(sc[8 * q + 1]) * inv);
+        o.y = ig::pack_bf16(__uint_as_float(sc[8 * q + 2]) * inv, __uint_as_float(sc[8 * q + 3]) * inv);
+        o.z = ig::pack_bf16(__uint_as_float(sc[8 * q + 4]) * inv, __uint_as_float(sc[8 * q + 5]) * inv);
+        o.w = ig::pack_bf16(__uint_as_float(sc[8 * q + 6]) * inv, __uint_as_float(sc[8 * q + 7]) * inv);
         reinterpret_cast<uint4*>(orow)[q] = o;
       }
     }
