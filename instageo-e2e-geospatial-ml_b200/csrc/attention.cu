@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
                  __nv_bfloat16* __restrict__ out, int N, int D) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // offset arithmetic on the __shared__ array itself (not a round trip through uintptr_t) keeps the pointer in
+  // the shared address space: LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math
+  uint8_t* smem = smem_raw + ((1024u - (ig::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [3]

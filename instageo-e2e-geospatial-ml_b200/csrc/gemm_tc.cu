@@ -95,8 +95,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const Args a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // offset arithmetic on the __shared__ array itself (not a round trip through uintptr_t) keeps the pointer in
+  // the shared address space: LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math
+  uint8_t* smem = smem_raw + ((1024u - (ig::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stg_base = smem + SMEM_MAIN;
   float* w1s = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_STAGING);  // [N][NCP]
   float* exch = reinterpret_cast<float*>(stg_base);                         // [2][BM][NCP] (EPI_FINAL)

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(T_THREADS) stitch_tma_kernel(const __grid_cons
   constexpr int TR = 4 * RT;
   constexpr int STAGE_FLOATS = CH * TR * PITCH;
   extern __shared__ uint8_t smem_raw[];
-  float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  float* ring = reinterpret_cast<float*>(smem_raw + ((128u - (ig::smem_u32(smem_raw) & 127u)) & 127u));
   __shared__ int s_xs[MAX_AX];
   __shared__ int s_ys[MAX_AX];
   __shared__ uint8_t s_cx[SEG];   // windows covering each pixel column of the tile
