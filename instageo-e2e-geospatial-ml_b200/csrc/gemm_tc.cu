@@ -84,6 +84,20 @@ __device__ __forceinline__ RowInfo make_row(const Args& a, int r, int phase) {
   return ri;
 }
 
+// Tile order of the persistent loop: output-parity phase fastest, then N tile, then M tile.  The CTA pairs
+// that run at the same time therefore work on the SAME rows of A (all phases and N tiles of one M tile),
+// which they find in L2.  With the phase outermost the transposed convolutions streamed their whole input
+// once per phase: 0.95 GB of DRAM reads per launch on average (2 GB at the 112 -> 224 stage, whose input
+// alone is 479 MB) instead of one pass.  The phase is rotated by the M tile so that a pair's tiles cycle
+// through the 1-, 2-, 2- and 4-tap phases instead of always getting the same two.
+__device__ __forceinline__ void decode_tile(const Args& a, int tile, int& phase, int& mt, int& nt) {
+  const int ph0 = tile % a.num_phases;
+  const int rest = tile / a.num_phases;
+  nt = rest % a.num_n_tiles;
+  mt = rest / a.num_n_tiles;
+  phase = (ph0 + mt) % a.num_phases;
+}
+
 // 16-byte chunk `chunk` of staging row `row`, XOR-swizzled so that both the row-per-thread writes and
 // the 4-rows-per-instruction read-back are bank-conflict free.
 __device__ __forceinline__ uint4* stg_slot(uint8_t* stg, int row, int chunk) {
@@ -148,10 +162,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t ph = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const int phase = tile / tiles_per_phase;
-        const int rem = tile - phase * tiles_per_phase;
-        const int m0 = (rem / a.num_n_tiles) * PAIR_M + static_cast<int>(rank) * BM;
-        const int nb0 = (rem % a.num_n_tiles) * a.block_n + static_cast<int>(rank) * half_n;
+        int phase, mt, nt;
+        decode_tile(a, tile, phase, mt, nt);
+        const int m0 = mt * PAIR_M + static_cast<int>(rank) * BM;
+        const int nb0 = nt * a.block_n + static_cast<int>(rank) * half_n;
         const Taps& tp = a.taps[phase];
         for (int t = 0; t < tp.n; ++t) {
           const TapGroup& tg = tp.g[t];
@@ -187,7 +201,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0;
       uint32_t acc_ph = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const int phase = tile / tiles_per_phase;
+        int phase, mt, nt;
+        decode_tile(a, tile, phase, mt, nt);
         const Taps& tp = a.taps[phase];
         ig::mbar_wait(&tempty[acc], acc_ph ^ 1);
         ig::tc_fence_after();
@@ -255,10 +270,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_ph = 0;
     int tile_par = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs) {
-      const int phase = tile / tiles_per_phase;
-      const int rem = tile - phase * tiles_per_phase;
-      const int m0 = (rem / a.num_n_tiles) * PAIR_M + static_cast<int>(rank) * BM;
-      const int n0 = (rem % a.num_n_tiles) * a.block_n;
+      int phase, mt, nt;
+      decode_tile(a, tile, phase, mt, nt);
+      const int m0 = mt * PAIR_M + static_cast<int>(rank) * BM;
+      const int n0 = nt * a.block_n;
       const int row_in_tile = quad * 32 + lane;
       const int r = m0 + row_in_tile;
       const RowInfo ri = make_row<EPI>(a, r, phase);
