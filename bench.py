@@ -47,6 +47,25 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def gemm_traffic_from_profile():
+    """Average DRAM bytes (read + write) per gemm_kernel launch of one bench step, from the committed ncu launch
+    list of this same command (profiles/r01_launches_bench_step.csv: --metrics gpu__time_duration.sum,
+    dram__bytes_read.sum,dram__bytes_write.sum).  None when the list is absent or has no DRAM columns."""
+    path = os.path.join(ROOT, "profiles", "r01_launches_bench_step.csv")
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import launch_summary
+        seq = launch_summary.load(path)
+        idx = [i for i, x in enumerate(seq) if "preprocess" in x["k"]]
+        step = seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq
+        g = [x for x in step if "gemm_kernel" in x["k"] and "dram__bytes_read.sum" in x]
+        if not g:
+            return None
+        return sum(x["dram__bytes_read.sum"] + x["dram__bytes_write.sum"] for x in g) / len(g)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -151,8 +170,10 @@ def run_tile(args):
     yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
     tile[:, (yy + xx) < 700] = -9999  # diagonal nodata wedge, like the corner of an HLS tile
     d_tile = tile.to(dev)
-    kw = dict(window_size=(224, 224), stride=args.stride, batch_size=64, mean=mean, std=std,
-              constant_multiplier=1e-4, no_data_value=-9999)
+    # the nodata comparison happens AFTER the constant multiplier (dataloader.py:741, 899 -- SURVEY F10), so the
+    # tile is normalised in raw DN units (statistics x 1e4, multiplier 1.0) to keep -9999 recognisable
+    kw = dict(window_size=(224, 224), stride=args.stride, batch_size=64, mean=[m * 1e4 for m in mean],
+              std=[s * 1e4 for s in std], constant_multiplier=1.0, no_data_value=-9999)
     n_win_total = len(ops.window_origins(H, 224, args.stride, True)) ** 2
 
     def step():
@@ -322,7 +343,10 @@ def main():
     all_ms = sum(v[0] for v in fam.values())
     roofline = {"kernel": "gemm_kernel<EPI> (tcgen05 GEMM: encoder linears + head implicit-GEMM convs)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_tf, "traffic": gemm_traffic_from_profile() if args.workload == "chips_v1_100m_t3" else None,
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the "
+                                "57 gemm_kernel launches of one step, profiles/r01_launches_bench_step.csv)",
+                "peak_source": peak_src,
                 "algorithmic_flops_per_launch": gemm_fl_step * args.steps / max(1, gemm_launches),
                 "avg_launch_ms": gemm_ms / max(1, gemm_launches), "share_of_step": gemm_ms / all_ms if all_ms else None,
                 "timing": "cuda events around every launch, %d instrumented steps right after the timed region" % args.steps}

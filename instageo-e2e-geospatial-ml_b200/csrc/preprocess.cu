@@ -272,13 +272,70 @@ __device__ __forceinline__ int raw_at(const uint4& q, int i) {
   return static_cast<int>(static_cast<RawT>(h));
 }
 
+// One timestep-band vector (8 pixels) of the fast path.  SAFE: every divisor of the launch admits the FMA
+// division (decided once per block), so the element loop has no branches at all.
+template <typename RawT, bool CM1, bool SAFE>
+__device__ __forceinline__ void band8(const PreArgs& a, const uint4& rv, float mean, float db, float dy,
+                                      uint32_t nd_bits, float (&o)[VEC], uint32_t& m) {
+  constexpr bool kSigned = static_cast<RawT>(-1) < static_cast<RawT>(0);
+  constexpr uint32_t kMagic = 0x4B000000u | (kSigned ? 0x8000u : 0u);   // 2^23, int16 sign bit flipped
+  const float kBias = kSigned ? 8421376.f : 8388608.f;                  // 2^23 (+ 2^15)
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float f;
+    if (CM1) {
+      // int16 / uint16 -> f32 without I2F (quarter-rate XU pipe): drop the 16 bits into the mantissa of
+      // 2^23 (sign bit flipped for int16: x + 32768 is unsigned) and subtract the offset; both steps exact.
+      // The nodata compare is done on the same bit pattern.
+      const uint32_t wd = (i < 2) ? rv.x : (i < 4) ? rv.y : (i < 6) ? rv.z : rv.w;
+      const uint32_t bits = ((i & 1) ? (wd >> 16) : (wd & 0xffffu)) ^ kMagic;
+      f = __fsub_rn(__uint_as_float(bits), kBias);
+      if (a.has_nodata && bits == nd_bits) m |= (1u << i);
+    } else {
+      const int rr = raw_at<RawT>(rv, i);
+      const double d = __dmul_rn(static_cast<double>(rr), a.cm);
+      f = __double2float_rn(d);
+      if (a.has_nodata && d == a.nodata) m |= (1u << i);
+    }
+    const float num = __fsub_rn(f, mean);
+    if (SAFE) {
+      float q = __fmul_rn(num, dy);
+      float r = __fmaf_rn(-db, q, num);
+      q = __fmaf_rn(r, dy, q);
+      r = __fmaf_rn(-db, q, num);
+      o[i] = __fmaf_rn(r, dy, q);
+    } else {
+      o[i] = __fdiv_rn(num, db);
+    }
+  }
+}
+
 template <typename RawT, bool CM1>
-__global__ void __launch_bounds__(256, 4) preprocess_i16x6_kernel(const PreArgs a) {
+__global__ void __launch_bounds__(256, 4) preprocess_i16x6_kernel(const __grid_constant__ PreArgs a) {
   constexpr int C = 6;
+  constexpr bool kSigned = static_cast<RawT>(-1) < static_cast<RawT>(0);
+  constexpr uint32_t kMagic = 0x4B000000u | (kSigned ? 0x8000u : 0u);
+  // per-band constants once per block: mean, divisor, its correctly rounded reciprocal, band offsets
+  __shared__ float s_mean[C], s_b[C], s_y[C];
+  __shared__ int64_t s_boff[MAX_TC];
+  __shared__ int s_safe;
+  if (threadIdx.x == 0) s_safe = 1;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const DivC d = make_div(__ldg(a.std + threadIdx.x));
+    s_mean[threadIdx.x] = __ldg(a.mean + threadIdx.x);
+    s_b[threadIdx.x] = d.b;
+    s_y[threadIdx.x] = d.y;
+    if (!d.safe) s_safe = 0;
+  }
+  if (threadIdx.x < a.T * C) s_boff[threadIdx.x] = __ldg(a.band_idx + threadIdx.x) * a.band_stride;
+  __syncthreads();
+  const bool safe = s_safe != 0;
   const int groups_per_row = a.win / VEC;
   const int64_t total = static_cast<int64_t>(a.n_win) * a.win * groups_per_row;
   const int gp = a.win / 16;
   const RawT* raw = static_cast<const RawT*>(a.raw);
+  const uint32_t nd_bits = (static_cast<uint32_t>(a.nodata_i) & 0xffffu) ^ kMagic;
   for (int64_t item = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; item < total;
        item += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(item % groups_per_row);
@@ -297,27 +354,13 @@ __global__ void __launch_bounds__(256, 4) preprocess_i16x6_kernel(const PreArgs 
     for (int t = 0; t < a.T; ++t) {
       uint4 rv[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) rv[c] = load_raw8<RawT>(src0 + __ldg(a.band_idx + t * C + c) * a.band_stride);
+      for (int c = 0; c < C; ++c) rv[c] = load_raw8<RawT>(src0 + s_boff[t * C + c]);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float mean = __ldg(a.mean + c);
-        const DivC dv = make_div(__ldg(a.std + c));
         float o[VEC];
         uint32_t m = 0;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const int rr = raw_at<RawT>(rv[c], i);
-          float f;
-          if (CM1) {
-            f = static_cast<float>(rr);
-            if (a.has_nodata && rr == a.nodata_i) m |= (1u << i);
-          } else {
-            const double d = __dmul_rn(static_cast<double>(rr), a.cm);
-            f = __double2float_rn(d);
-            if (a.has_nodata && d == a.nodata) m |= (1u << i);
-          }
-          o[i] = div_by(__fsub_rn(f, mean), dv);
-        }
+        if (safe) band8<RawT, CM1, true>(a, rv[c], s_mean[c], s_b[c], s_y[c], nd_bits, o, m);
+        else band8<RawT, CM1, false>(a, rv[c], s_mean[c], s_b[c], s_y[c], nd_bits, o, m);
         any_nodata |= m;
         if (a.out_f32) {
           float* dst = a.out_f32 + (((static_cast<int64_t>(w) * C + c) * a.T + t) * a.win + y) * a.win + x;
@@ -433,8 +476,11 @@ extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_sr
     // never equal an int16/uint16 sample, so with constant_multiplier == 1 the mask is simply empty
     PreArgs f = a;
     if (f.cm_is_one && f.has_nodata) {
-      if (no_data_value == floor(no_data_value) && fabs(no_data_value) < 1e9) f.nodata_i = static_cast<int>(no_data_value);
-      else f.has_nodata = 0;
+      const double lo = raw_dtype == IG_I16 ? -32768.0 : 0.0, hi = raw_dtype == IG_I16 ? 32767.0 : 65535.0;
+      if (no_data_value == floor(no_data_value) && no_data_value >= lo && no_data_value <= hi)
+        f.nodata_i = static_cast<int>(no_data_value);  // compared as a 16-bit pattern by the fast kernel
+      else
+        f.has_nodata = 0;                              // not representable in the raw type: never equal
     }
     // (the generic kernel keeps the float64 compare, so only hand it the adjusted args on the fast path)
     const bool fastable = f.C == 6 && f.fmask == nullptr;
