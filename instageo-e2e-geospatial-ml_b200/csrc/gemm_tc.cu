@@ -287,21 +287,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       __syncwarp();
-      if (EPI == EPI_RESID && ri.valid) {
-        // the residual tile does not depend on the MMAs: pull this thread's row pieces into L2 while
-        // the tensor core is still working on the tile
-        const float* rrow = a.resid + static_cast<long long>(ri.orow) * a.ldo + n0;
-        for (int g = half; g < ngroups; g += 2)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + g * GC));
+      // element offset of this thread's output row (+ n0), -1 = row is not stored
+      const bool store_row = (EPI == EPI_CONVT) ? ri.interior : ri.valid;
+      const long long obase = store_row ? static_cast<long long>(ri.orow) * a.ldo + n0 : -1ll;
+      // The residual tile does not depend on the MMAs.  Its pieces for the warp's NEXT column group are always
+      // in flight: the first group's are requested here, before the accumulator wait (and the later groups'
+      // rows are pulled into L2), group g+2's right after group g has been written out -- so their latency
+      // hides under the tensor core and under the TMEM load / bias / staging of the group in between,
+      // instead of being exposed once per group (4x per tile).
+      float4 extra[8];
+      auto load_resid = [&](int g) {
+        const int col0 = g * GC;
+        const int gcols = (a.block_n - col0) < GC ? (a.block_n - col0) : GC;
+        const int nchunk = gcols / EPC, ch = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const long long ob = __shfl_sync(0xffffffffu, obase, it * 4 + (lane >> 3));
+          extra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ob >= 0 && ch < nchunk) extra[it] = *reinterpret_cast<const float4*>(a.resid + ob + col0 + ch * EPC);
+        }
+      };
+      if (EPI == EPI_RESID) {
+        if (half < ngroups) load_resid(half);
+        if (ri.valid) {
+          const float* rrow = a.resid + static_cast<long long>(ri.orow) * a.ldo + n0;
+          for (int g = half + 2; g < ngroups; g += 2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + g * GC));
+        }
       }
       ig::mbar_wait(&tfull[acc], acc_ph);
       ig::tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * MAX_BN;
 
       if (EPI != EPI_FINAL) {
-        // element offset of this thread's output row (+ n0), -1 = row is not stored
-        const bool store_row = (EPI == EPI_CONVT) ? ri.interior : ri.valid;
-        const long long obase = store_row ? static_cast<long long>(ri.orow) * a.ldo + n0 : -1ll;
         bool released = false;
         for (int g = half; g < ngroups; g += 2) {
           const int col0 = g * GC;
@@ -376,7 +394,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int nchunk = gcols / EPC;
           const int ch = lane & 7;
           long long offs[8];
-          float4 extra[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + (lane >> 3);
@@ -384,11 +401,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int tok = (EPI == EPI_PATCH) ? __shfl_sync(0xffffffffu, ri.xx, row) : 0;
             const bool ok = ob >= 0 && ch < nchunk;
             offs[it] = ok ? ob + col0 + ch * EPC : -1ll;
-            extra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (EPI == EPI_RESID && ok) extra[it] = *reinterpret_cast<const float4*>(a.resid + offs[it]);
-            if (EPI == EPI_PATCH && ok)
-              extra[it] = __ldg(reinterpret_cast<const float4*>(
-                  a.pos + static_cast<int64_t>(1 + tok) * a.N + n0 + col0 + ch * EPC));
+            if (EPI == EPI_PATCH) {
+              extra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok)
+                extra[it] = __ldg(reinterpret_cast<const float4*>(
+                    a.pos + static_cast<int64_t>(1 + tok) * a.N + n0 + col0 + ch * EPC));
+            }
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -407,6 +425,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + offs[it]) = q;
             }
           }
+          if (EPI == EPI_RESID && g + 2 < ngroups) load_resid(g + 2);  // other columns than the stores above
           __syncwarp();
         }
         if (!released) {  // warp had no column group in this tile (ngroups == 1, half == 1)
