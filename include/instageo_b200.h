@@ -43,6 +43,10 @@ extern "C" {
 #define IG_I16 2
 #define IG_U16 3
 #define IG_F64 4 /* ig_preprocess raw input only: already-scaled float64 host arrays */
+#define IG_I64 5 /* label element types of the metric kernels */
+#define IG_I32 6
+#define IG_U8 7
+#define IG_I8 8
 
 /* masking strategies, instageo/data/data_pipeline.py:254-267 */
 #define IG_MASK_EACH 0
@@ -159,6 +163,73 @@ int ig_layernorm(const float* x, const float* gamma, const float* beta, void* ou
                  void* stream);
 /* qkv bf16 [B*N, 3*D] (timm layout: q | k | v, head-major inside) -> out bf16 [B*N, D] */
 int ig_attention(const void* qkv, void* out, int B, int N, int heads, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Chip-creation masking at tile scale, one pass instead of the reference's
+ * xarray chain in HLSRasterPipeline (instageo/data/hls_utils.py:359-403):
+ *   apply_mask + decode_fmask_value   instageo/data/data_pipeline.py:229-267, hls_utils.py:77-86
+ *   chip.clip(0, 10000), astype(uint16)                    hls_utils.py:371-373, :386, :401
+ *   mask_segmentation_map, astype(int8)                    data_pipeline.py:66-98, hls_utils.py:392-400
+ *   the two "skip if nothing is left" counts               hls_utils.py:389, :395
+ *
+ * chip      [n_bands, H, W] int16 | uint16, dense.   fmask [n_mask_steps, H, W] uint8 or NULL; band b
+ *           uses mask step b / (n_bands / n_mask_steps) (strategy each) or the OR of all steps (any);
+ *           a pixel is masked when any bit of fmask_bits is set in its Fmask byte, and becomes
+ *           no_data_value.  Then values are clipped to [clip_min, clip_max] (clip_min > clip_max: no
+ *           clipping) and written to out [n_bands, H, W] (uint16; the input's type when not clipping).
+ * seg_map   [H, W] int8 or NULL: pixels whose chip is no_data_value in every band (strategy each) or
+ *           in at least one band (any) become seg_no_data_value in seg_out [H, W].
+ * counts    [2] uint64 or NULL, accumulated: [0] += chip elements != no_data_value after clipping,
+ *           [1] += label pixels != seg_no_data_value.
+ */
+int ig_chip_mask(const void* chip, int chip_dtype, int n_bands, int64_t height, int64_t width,
+                 const uint8_t* fmask, int n_mask_steps, uint32_t fmask_bits, int masking_strategy,
+                 int no_data_value, int clip_min, int clip_max, uint16_t* out, const int8_t* seg_map,
+                 int seg_masking_strategy, int seg_no_data_value, int8_t* seg_out,
+                 unsigned long long* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Eval-mode streaming metrics accumulated on the device.
+ * Replaces the per-step host round trip of
+ *   RunningConfusionMatrix.update   instageo/model/metrics.py:86-108
+ *   RunningAUC.update / _bin        instageo/model/metrics.py:209-244
+ *   RunningRegressionMetrics.update instageo/model/metrics.py:330-356
+ * as driven by PrithviSegmentationModule._shared_step, instageo/model/segmentation.py:117-156
+ * (argmax, softmax, ignore_index gather, three D2H copies, np.bincount / np.add.at).
+ * All outputs are ACCUMULATED (+=) into caller-owned, zero-initialised device buffers.
+ *
+ * labels      [n] int64 | int32 | uint8 | int8 (label_dtype IG_I64 ...); has_ignore != 0 drops
+ *             elements equal to ignore_index (before any range check, like the reference's mask).
+ * matrix      [k*k] uint64, row = truth, column = prediction.
+ * counters    [2] uint64: [0] += valid samples (RunningConfusionMatrix.total), [1] += samples whose
+ *             label or prediction is outside [0, k) -- the reference raises ValueError there
+ *             (np.bincount / reshape); the host mirror raises when it reads a non-zero counter.
+ */
+int ig_confusion_update(const int8_t* pred, const void* labels, int label_dtype, int64_t n,
+                        int num_classes, int has_ignore, int64_t ignore_index,
+                        unsigned long long* matrix, unsigned long long* counters, void* stream);
+/* Fused eval step from logits f32 [n_img, nc, hw] (NCHW; hw % 4 == 0) and labels [n_img, hw]:
+ * first-max argmax -> matrix (may be NULL), float32 softmax over classes -> one-vs-rest score
+ * histograms pos_hist / neg_hist [nc, n_bins] uint64 (both NULL to skip), binned with the
+ * reference's float32 arithmetic trunc((s - min) / (max - min) * (n_bins - 1)) after clamping.
+ * Labels outside [0, nc) that are not ignored count as negatives of every class (as in
+ * RunningAUC.update) and in counters[1]. */
+int ig_seg_metrics_update(const float* logits, int64_t n_img, int num_classes, int64_t hw,
+                          const void* labels, int label_dtype, int has_ignore, int64_t ignore_index,
+                          unsigned long long* matrix, unsigned long long* counters, int n_bins,
+                          float min_score, float max_score, unsigned long long* pos_hist,
+                          unsigned long long* neg_hist, void* stream);
+/* RunningAUC.update on given probabilities: scores [n, k] row-major float32 | float64 (binned in the
+ * scores' own precision, as numpy >= 2 scalar arithmetic does in RunningAUC._bin), labels [n]. */
+int ig_auc_update(const void* scores, int score_dtype, int64_t n, int num_classes, const void* labels,
+                  int label_dtype, int n_bins, double min_score, double max_score,
+                  unsigned long long* pos_hist, unsigned long long* neg_hist, void* stream);
+/* sums [7] float64 += (x, y, xy, x^2, y^2, |y-x|, (y-x)^2) with x = y_true, y = y_pred;
+ * counts [2] uint64 += (n, |y-x| <= ee_bias + ee_coef*x evaluated in float32 like the reference).
+ * has_ignore drops elements whose y_true == ignore_value (regression.py:154). */
+int ig_regression_update(const float* y_true, const float* y_pred, int64_t n, int has_ignore,
+                         float ignore_value, float ee_bias, float ee_coef, double* sums,
+                         unsigned long long* counts, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Measurement aid (bench.py roofline): when enabled, every launch is bracketed by CUDA events on

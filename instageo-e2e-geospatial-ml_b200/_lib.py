@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinstageo_b200.so")
 
 IG_F32, IG_BF16, IG_I16, IG_U16, IG_F64 = 0, 1, 2, 3, 4
+IG_I64, IG_I32, IG_U8, IG_I8 = 5, 6, 7, 8
 IG_MASK_EACH, IG_MASK_ANY = 0, 1
 ERRORS = {-1: "IG_EINVAL", -2: "IG_ESHAPE", -3: "IG_ECUDA", -4: "IG_ENOMEM", -5: "IG_EARCH", -6: "IG_ESTATE"}
 
@@ -30,7 +31,7 @@ class ModelCfg(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/instageo_b200.h declares
-_P, _I, _I64, _D, _SZ, _U32 = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t, C.c_uint32
+_P, _I, _I64, _D, _SZ, _U32, _F = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t, C.c_uint32, C.c_float
 SIGNATURES = {
     "ig_version": (_I, []),
     "ig_last_error": (C.c_char_p, []),
@@ -48,6 +49,11 @@ SIGNATURES = {
     "ig_linear": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ig_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ig_attention": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ig_chip_mask": (_I, [_P, _I, _I, _I64, _I64, _P, _I, _U32, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
+    "ig_confusion_update": (_I, [_P, _P, _I, _I64, _I, _I, _I64, _P, _P, _P]),
+    "ig_seg_metrics_update": (_I, [_P, _I64, _I, _I64, _P, _I, _I, _I64, _P, _P, _I, _F, _F, _P, _P, _P]),
+    "ig_auc_update": (_I, [_P, _I, _I64, _I, _P, _I, _I, _D, _D, _P, _P, _P]),
+    "ig_regression_update": (_I, [_P, _P, _I64, _I, _F, _F, _F, _P, _P, _P]),
     "ig_profile_enable": (_I, [_I]),
     "ig_profile_report": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int), _I]),
 }

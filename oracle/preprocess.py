@@ -140,6 +140,24 @@ def mask_segmentation_map(chip: np.ndarray, seg_map: np.ndarray, chip_no_data_va
     return np.where(valid, seg_map, seg_no_data_value)
 
 
+def create_chip(chip: np.ndarray, fmask, seg_map=None, strategy="each", mask_types=tuple(HLS_FMASK_POS.keys()),
+                no_data_value=0, clip=(0, 10000), seg_no_data_value=-1):
+    """The array arithmetic of ``HLSRasterPipeline`` chip creation, hls_utils.py:359-403, on plain arrays:
+    apply_mask (fill 0) -> clip(0, 10000) -> "all cloud?" count -> mask_segmentation_map on the clipped chip
+    -> "empty label?" count -> uint16 chip / int8 label map.
+    Returns (chip uint16, seg int8 or None, n_valid_chip_elements, n_valid_label_pixels or None)."""
+    out = chip.astype(np.int64)
+    if fmask is not None:
+        out = apply_fmask(out, fmask, no_data_value, strategy, mask_types)
+    if clip is not None:
+        out = np.clip(out, clip[0], clip[1])
+    n_valid = int((out != no_data_value).sum())
+    if seg_map is None:
+        return out.astype(np.uint16), None, n_valid, None
+    seg = mask_segmentation_map(out, seg_map, no_data_value, strategy, seg_no_data_value)
+    return out.astype(np.uint16), seg.astype(np.int8), n_valid, int((seg != seg_no_data_value).sum())
+
+
 # ----------------------------------------------------------------------------- synthetic inputs
 def synth_chips(n: int, temporal: int, seed: int = 1042, size: int = 224, nodata=-9999,
                 dtype=np.int16, n_src_bands: int | None = None) -> np.ndarray:
