@@ -141,6 +141,11 @@ size_t ig_model_workspace_bytes(const ig_model* m, int batch);
 int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits,
                      int8_t* argmax, float* feats, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* PrithviSegmentationModule.predict_step (instageo/model/segmentation.py:202-213):
+ * prob_pos [B, 224, 224] float32 = softmax(logits, dim=1)[:, 1], computed in the head epilogue
+ * (logits never stored).  num_classes >= 2. */
+int ig_model_predict_proba(ig_model* m, const void* x, int x_dtype, int batch, float* prob_pos,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernel launches one ig_model_forward enqueues (for bench accounting) */
 int ig_model_launches_per_forward(const ig_model* m);
 /* debug / parity taps: copy an intermediate activation of the LAST forward as float32.

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ig_model_finalize": (_I, [_P, _P]),
     "ig_model_workspace_bytes": (_SZ, [_P, _I]),
     "ig_model_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "ig_model_predict_proba": (_I, [_P, _P, _I, _I, _P, _P, _SZ, _P]),
     "ig_model_launches_per_forward": (_I, [_P]),
     "ig_model_debug_tap": (_I, [_P, C.c_char_p, _I, _P, _P, _SZ, _P]),
     "ig_model_destroy": (_I, [_P]),

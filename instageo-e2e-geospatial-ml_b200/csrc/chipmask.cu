@@ -140,6 +140,111 @@ __global__ void __launch_bounds__(THREADS) chip_mask_kernel(const MaskArgs a) {
   }
 }
 
+// Vector kernel: one thread = 8 consecutive pixels = one 16-byte vector per band, arithmetic on packed
+// int16x2 words (VIMNMX.S16x2 / .U16x2 are native on sm_100): per pixel PAIR one LOP3 to substitute the
+// fill value under the cloud mask, a packed min and max for the clip, a packed compare against the fill
+// value whose lane masks feed the any/all-band label rule (OR / AND) and the valid-element count (POPC).
+// The cloud bits of the <= 8 mask steps live in one 64-bit register (byte t = the 8 pixels of step t) and
+// are expanded to lane masks only when the band's step changes (a warp-uniform branch).
+template <bool SIGNED>
+__global__ void __launch_bounds__(THREADS) chip_mask_vec_kernel(const MaskArgs a, uint32_t nd2, uint32_t lo2,
+                                                                uint32_t hi2, int nd_reachable) {
+  const long long nvec = a.P >> 3;
+  const int per_step = a.n_bands / a.n_steps;
+  uint32_t kept_bits = 0;  // 16 per valid element
+  unsigned long long kept = 0, lab_kept = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * THREADS) {
+    const long long p0 = i << 3;
+    unsigned long long cbits = 0;
+    if (a.fmask) {
+      uint32_t any8 = 0;
+      for (int t = 0; t < a.n_steps; ++t) {
+        const uint2 f = __ldcs(reinterpret_cast<const uint2*>(a.fmask + t * a.P + p0));
+        // byte j of (f & bits) non-zero -> bit j
+        const uint32_t bx = f.x & (a.bits * 0x01010101u), by = f.y & (a.bits * 0x01010101u);
+        uint32_t m8 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m8 |= ((bx >> (8 * j)) & 0xffu) ? (1u << j) : 0u;
+          m8 |= ((by >> (8 * j)) & 0xffu) ? (16u << j) : 0u;
+        }
+        cbits |= static_cast<unsigned long long>(m8) << (8 * t);
+        any8 |= m8;
+      }
+      if (a.strategy == IG_MASK_ANY) cbits = any8 * 0x0101010101010101ull;
+    }
+    uint32_t cm[4] = {0, 0, 0, 0};
+    int t_cur = -1;
+    uint32_t any_valid[4] = {0, 0, 0, 0}, all_valid[4] = {~0u, ~0u, ~0u, ~0u};
+    constexpr int BG = 6;
+    for (int b0 = 0; b0 < a.n_bands; b0 += BG) {
+      uint4 raw[BG];
+#pragma unroll
+      for (int u = 0; u < BG; ++u)
+        if (b0 + u < a.n_bands)
+          raw[u] = __ldcs(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.chip) + (b0 + u) * a.P + p0));
+#pragma unroll
+      for (int u = 0; u < BG; ++u) {
+        if (b0 + u < a.n_bands) {
+          const int b = b0 + u, t = b / per_step;
+          if (t != t_cur) {
+            t_cur = t;
+            const uint32_t m8 = static_cast<uint32_t>(cbits >> (8 * t)) & 0xffu;
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              cm[w] = ((m8 >> (2 * w)) & 1u ? 0x0000ffffu : 0u) | ((m8 >> (2 * w + 1)) & 1u ? 0xffff0000u : 0u);
+          }
+          uint32_t x[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            uint32_t v = (x[w] & ~cm[w]) | (nd2 & cm[w]);
+            v = SIGNED ? __vmaxs2(__vmins2(v, hi2), lo2) : __vmaxu2(__vminu2(v, hi2), lo2);
+            const uint32_t ne = nd_reachable ? __vcmpne2(v, nd2) : 0xffffffffu;
+            kept_bits += __popc(ne);
+            any_valid[w] |= ne;
+            all_valid[w] &= ne;
+            x[w] = v;
+          }
+          __stcs(reinterpret_cast<uint4*>(a.out + b * a.P + p0), make_uint4(x[0], x[1], x[2], x[3]));
+        }
+      }
+    }
+    kept += kept_bits >> 4;
+    kept_bits = 0;
+    if (a.seg_in) {
+      const uint2 sv = __ldcs(reinterpret_cast<const uint2*>(a.seg_in + p0));
+      uint32_t sw[2] = {sv.x, sv.y};
+      const uint32_t fill = static_cast<uint32_t>(static_cast<uint8_t>(a.seg_no_data)) * 0x01010101u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // lane masks of pixels (4h .. 4h+3) -> byte masks
+        const uint32_t* src = a.seg_strategy == IG_MASK_EACH ? any_valid : all_valid;
+        const uint32_t l0 = src[2 * h], l1 = src[2 * h + 1];
+        const uint32_t ok = (l0 & 0x000000ffu) | ((l0 >> 8) & 0x0000ff00u) | ((l1 << 16) & 0x00ff0000u) | (l1 & 0xff000000u);
+        sw[h] = (sw[h] & ok) | (fill & ~ok);
+        lab_kept += __popc(__vcmpne4(sw[h], fill)) >> 3;
+      }
+      __stcs(reinterpret_cast<uint2*>(a.seg_out + p0), make_uint2(sw[0], sw[1]));
+    }
+  }
+  if (a.counts) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kept += __shfl_xor_sync(0xffffffffu, kept, o);
+      lab_kept += __shfl_xor_sync(0xffffffffu, lab_kept, o);
+    }
+    __shared__ unsigned long long red[2][THREADS / 32];
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = kept, red[1][threadIdx.x >> 5] = lab_kept;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      unsigned long long t = 0;
+      for (int w = 0; w < THREADS / 32; ++w) t += red[threadIdx.x][w];
+      if (t) atomicAdd(a.counts + threadIdx.x, t);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int ig_chip_mask(const void* chip, int chip_dtype, int n_bands, int64_t height, int64_t width,
@@ -175,7 +280,7 @@ extern "C" int ig_chip_mask(const void* chip, int chip_dtype, int n_bands, int64
   a.out = out, a.seg_in = seg_map, a.seg_strategy = seg_masking_strategy, a.seg_no_data = seg_no_data_value;
   a.seg_out = seg_out, a.counts = counts;
   auto al = [](const void* p, int n) { return (reinterpret_cast<uintptr_t>(p) & (n - 1)) == 0; };
-  const bool vec = P % 8 == 0 && al(chip, 16) && al(out, 16) && (!use_fmask || al(fmask, 8)) &&
+  const bool vec = P % 8 == 0 && al(chip, 16) && al(out, 16) && (!use_fmask || (al(fmask, 8) && n_mask_steps <= 8)) &&
                    (!seg_map || (al(seg_map, 8) && al(seg_out, 8)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long work = vec ? P / 8 : P;
@@ -183,9 +288,28 @@ extern "C" int ig_chip_mask(const void* chip, int chip_dtype, int n_bands, int64
   const long long cap = 8ll * ig_num_sms();
   if (blocks > cap) blocks = cap;
   ig::ProfScope prof(ig::PROF_PREPROCESS, st);
-  if (vec)
-    chip_mask_kernel<8><<<static_cast<unsigned>(blocks), THREADS, 0, st>>>(a);
-  else
+  if (vec) {
+    // the fill value as the kernel's 16-bit lanes see it: substituted BEFORE the clip, compared AFTER it
+    const int type_lo = a.chip_is_signed ? -32768 : 0, type_hi = a.chip_is_signed ? 32767 : 65535;
+    const int nd_in = no_data_value < type_lo ? type_lo : (no_data_value > type_hi ? type_hi : no_data_value);
+    const int nd_after = nd_in < clip_min ? clip_min : (nd_in > clip_max ? clip_max : nd_in);
+    // a fill value outside the input type saturates; it then behaves like the scalar path only if the clip maps
+    // both to the same number, which holds whenever it is representable or lies outside the clip range
+    const bool same = (no_data_value < clip_min ? clip_min : (no_data_value > clip_max ? clip_max : no_data_value)) == nd_after;
+    // clip bounds as 16-bit lanes of the input's type (same result for every representable input)
+    const int eff_lo = clip_min < type_lo ? type_lo : clip_min, eff_hi = clip_max > type_hi ? type_hi : clip_max;
+    if (same && eff_lo <= eff_hi) {
+      clip_min = eff_lo, clip_max = eff_hi;
+      auto pk = [](int v) { return (static_cast<uint32_t>(v) & 0xffffu) * 0x00010001u; };
+      const int reachable = no_data_value >= eff_lo && no_data_value <= eff_hi;  // else every element is valid
+      if (a.chip_is_signed)
+        chip_mask_vec_kernel<true><<<static_cast<unsigned>(blocks), THREADS, 0, st>>>(a, pk(nd_in), pk(clip_min), pk(clip_max), reachable);
+      else
+        chip_mask_vec_kernel<false><<<static_cast<unsigned>(blocks), THREADS, 0, st>>>(a, pk(nd_in), pk(clip_min), pk(clip_max), reachable);
+    } else {
+      chip_mask_kernel<8><<<static_cast<unsigned>(blocks), THREADS, 0, st>>>(a);
+    }
+  } else
     chip_mask_kernel<1><<<static_cast<unsigned>(blocks), THREADS, 0, st>>>(a);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;

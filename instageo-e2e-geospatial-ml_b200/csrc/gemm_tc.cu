@@ -488,6 +488,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < NCP; ++k) {
             if (k < a.nc) {
               const float lv = logit[k] + ex[k] + __ldg(a.b1 + k);
+              logit[k] = lv;
               if (a.logits) a.logits[(static_cast<int64_t>(ri.img) * a.nc + k) * H * W + px] = lv;
               if (k == 0 || lv > best) {
                 best = lv;
@@ -496,6 +497,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (a.argmax) a.argmax[static_cast<int64_t>(ri.img) * H * W + px] = static_cast<int8_t>(bi);
+          if (a.prob1) {  // predict_step: softmax over classes, channel 1 (float32, exp(x - max) / sum)
+            float den = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCP; ++k)
+              if (k < a.nc) den += expf(logit[k] - best);
+            a.prob1[static_cast<int64_t>(ri.img) * H * W + px] = __fdiv_rn(expf(logit[1] - best), den);
+          }
         }
         tile_par ^= 1;
       }

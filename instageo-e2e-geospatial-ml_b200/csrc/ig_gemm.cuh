@@ -64,6 +64,7 @@ struct Args {
   int nc;
   float* logits;          // [B, nc, H, W] or null
   int8_t* argmax;         // [B, H, W] or null
+  float* prob1;           // [B, H, W] or null: softmax(logits, dim=1)[:, 1] (segmentation.py:211-213)
 };
 
 struct Plan {

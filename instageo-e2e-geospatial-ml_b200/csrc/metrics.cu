@@ -13,8 +13,9 @@
 // Layout: logits f32 [n_img, nc, hw] (NCHW), labels [n_img, hw] (int64 as the reference's labels.long(),
 // or int32 / uint8 / int8), one thread = 4 consecutive pixels, float4 loads per class plane, all nc
 // planes requested before the first use.  Counters live in shared memory (u32) per block and are
-// flushed with one 64-bit global atomic per non-zero entry; same-warp collisions (softmax scores pile
-// up in bin 0 and bin n_bins-1) are merged with match.any before the shared atomic.
+// flushed with one 64-bit global atomic per non-zero entry.  Softmax scores pile up in bin 0 (negatives)
+// and bin n_bins-1 (positives): those two bins per class, and the sample counts, are counted in registers;
+// confusion-matrix cells (few keys, always contended) are merged across the warp with match.any.
 #include "ig_common.cuh"
 
 namespace {
@@ -78,7 +79,9 @@ __device__ __forceinline__ void warp_count(uint32_t* smem, uint32_t key, bool on
 __device__ __forceinline__ int score_bin(float s, float lo, float hi, float range, float nbm1, int n_bins) {
   if (!(s > lo)) return 0;
   if (s >= hi) return n_bins - 1;
-  const float x = __fmul_rn(__fdiv_rn(__fsub_rn(s, lo), range), nbm1);
+  // x / 1.0f == x: skip the division for the default [0, 1] range (a denormal score would take its slow path)
+  const float num = __fsub_rn(s, lo);
+  const float x = __fmul_rn(range == 1.0f ? num : __fdiv_rn(num, range), nbm1);
   return static_cast<int>(x);
 }
 
@@ -101,10 +104,44 @@ __global__ void __launch_bounds__(THREADS) seg_metrics_kernel(const SegArgs a) {
   const long long total_quads = a.n_img * quads_per_img;
   const float range = a.hi - a.lo, nbm1 = static_cast<float>(a.n_bins - 1);
   // a block's shared counters are u32: flush before any of them can wrap (every pixel adds at most 1 to a bin)
-  const long long flush_every = (1ll << 31) / (4ll * THREADS);
+  // ... and the 16-bit per-thread fields hold 4 pixels per iteration
+  const long long flush_every = 8192;
   long long iters = 0;
-
+  // Per-thread counters for what nearly every pixel hits: the valid / out-of-range sample counts and, for
+  // the ROC histograms, the first and the last bin of every class (softmax scores pile up at 0 and 1), kept
+  // as two 16-bit fields per register and warp-reduced into shared memory at flush time.  Every other bin
+  // takes a plain shared atomic (rarely contended: ~1 lane per clock per SM is all ATOMS delivers).
+  uint32_t n_ok = 0, n_bad = 0;
+  uint32_t hot_pos[NC > 0 ? NC : 1], hot_neg[NC > 0 ? NC : 1];  // [15:0] first bin, [31:16] last bin
+#pragma unroll
+  for (int c = 0; c < (NC > 0 ? NC : 1); ++c) hot_pos[c] = hot_neg[c] = 0;
   auto flush = [&]() {
+    {
+      const int lane = threadIdx.x & 31;
+      uint32_t t0 = n_ok, t1 = n_bad;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t0 += __shfl_xor_sync(0xffffffffu, t0, o), t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      if (lane == 0 && t0) atomicAdd(s_cnt, t0);
+      if (lane == 0 && t1) atomicAdd(s_cnt + 1, t1);
+      n_ok = n_bad = 0;
+      if (want_auc) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t u[4] = {hot_pos[c] & 0xffffu, hot_pos[c] >> 16, hot_neg[c] & 0xffffu, hot_neg[c] >> 16};
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) u[f] += __shfl_xor_sync(0xffffffffu, u[f], o);
+          if (lane == 0) {
+            if (u[0]) atomicAdd(s_pos + c * a.n_bins, u[0]);
+            if (u[1]) atomicAdd(s_pos + c * a.n_bins + (a.n_bins - 1), u[1]);
+            if (u[2]) atomicAdd(s_neg + c * a.n_bins, u[2]);
+            if (u[3]) atomicAdd(s_neg + c * a.n_bins + (a.n_bins - 1), u[3]);
+          }
+          hot_pos[c] = hot_neg[c] = 0;
+        }
+      }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n_sm; i += THREADS) {
       const uint32_t v = sm[i];
@@ -166,24 +203,33 @@ __global__ void __launch_bounds__(THREADS) seg_metrics_kernel(const SegArgs a) {
             prob[c] = expf(v[c][j] - m);
             s += prob[c];
           }
+          // e / s through the reciprocal and one FMA correction step (s is in [1, NC]): within 1 ulp of the
+          // true quotient like the exponentials feeding it, and free of __fdiv_rn's slow path, which every
+          // denormal numerator (confident models: exp(-90)) would take
+          const float r = __frcp_rn(s);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) prob[c] = __fdiv_rn(prob[c], s);
+          for (int c = 0; c < NC; ++c) {
+            const float q = prob[c] * r;
+            prob[c] = fmaf(fmaf(-q, s, prob[c]), r, q);
+          }
         }
       }
       const bool in_range = lab[j] >= 0 && lab[j] < a.k && prd[j] >= 0 && prd[j] < a.k;
       warp_count(s_conf, static_cast<uint32_t>(in_range ? lab[j] * a.k + prd[j] : 0), use && in_range);
-      warp_count(s_cnt, in_range ? 0u : 1u, use);
+      n_ok += use && in_range;
+      n_bad += use && !in_range;
       if (want_auc) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int b = score_bin(prob[c], a.lo, a.hi, range, nbm1, a.n_bins);
           const bool is_pos = lab[j] == c;
-          // one call for both histograms: they are adjacent in shared memory
-          warp_count(s_pos, static_cast<uint32_t>((is_pos ? 0 : NC * a.n_bins) + c * a.n_bins + b), use);
+          const uint32_t inc = !use ? 0u : (b == 0 ? 1u : (b == a.n_bins - 1 ? 0x10000u : 0u));
+          hot_pos[c] += is_pos ? inc : 0u;
+          hot_neg[c] += is_pos ? 0u : inc;
+          if (use && inc == 0u) atomicAdd((is_pos ? s_pos : s_neg) + c * a.n_bins + b, 1u);
         }
       }
     }
-    (void)s_neg;
     if (++iters == flush_every) {
       flush();
       iters = 0;
@@ -209,7 +255,7 @@ __global__ void __launch_bounds__(THREADS) confusion_elem_kernel(const SegArgs a
     const bool use = live && !(a.has_ignore && lab == a.ignore);
     const bool in_range = lab >= 0 && lab < a.k && prd >= 0 && prd < a.k;
     warp_count(sm, static_cast<uint32_t>(in_range ? lab * a.k + prd : 0), use && in_range);
-    warp_count(sm + kk, in_range ? 0u : 1u, use);
+    if (use) atomicAdd(sm + kk + (in_range ? 0 : 1), 1u);  // ragged tails only: a few elements
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kk + 2; i += THREADS) {

@@ -426,8 +426,8 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
 
 }  // namespace
 
-extern "C" int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits, int8_t* argmax,
-                                float* feats, void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_impl(ig_model* m, const void* x, int x_dtype, int batch, float* logits, int8_t* argmax,
+                        float* prob1, float* feats, void* workspace, size_t workspace_bytes, void* stream) {
   IG_TRY(ig_check_device());
   IG_REQUIRE(m && x && workspace, IG_EINVAL, "ig_model_forward: null pointer");
   IG_REQUIRE(m->finalized, IG_ESTATE, "ig_model_forward: call ig_model_finalize after loading weights");
@@ -526,10 +526,23 @@ extern "C" int ig_model_forward(ig_model* m, const void* x, int x_dtype, int bat
       p.args.nc = m->nc;
       p.args.logits = logits;
       p.args.argmax = (m->nc > 1) ? argmax : nullptr;
+      p.args.prob1 = prob1;
       IG_TRY(gemm::launch(p, st));
     }
   }
   return IG_OK;
+}
+
+extern "C" int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits, int8_t* argmax,
+                                float* feats, void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(m, x, x_dtype, batch, logits, argmax, nullptr, feats, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ig_model_predict_proba(ig_model* m, const void* x, int x_dtype, int batch, float* prob_pos,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  IG_REQUIRE(m && prob_pos, IG_EINVAL, "ig_model_predict_proba: null pointer");
+  IG_REQUIRE(m->nc >= 2, IG_ESHAPE, "ig_model_predict_proba: needs a classification head (num_classes >= 2)");
+  return forward_impl(m, x, x_dtype, batch, nullptr, nullptr, prob_pos, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ig_model_debug_tap(ig_model* m, const char* name, int batch, void* workspace, float* dst,

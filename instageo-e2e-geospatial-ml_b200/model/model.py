@@ -353,6 +353,28 @@ class PrithviSeg(nn.Module):
         return self._run(img, _lib.IG_F32, img.shape[0], False, True, False)[1]
 
     @torch.no_grad()
+    def predict_proba(self, img: torch.Tensor) -> torch.Tensor:
+        """``PrithviSegmentationModule.predict_step`` (instageo/model/segmentation.py:202-213):
+        ``softmax(logits, dim=1)[:, 1]`` float32 [B, H, W], fused into the head epilogue."""
+        if self.num_classes < 2:
+            raise RuntimeError("predict_proba() needs a classification head; a regression head's "
+                               "predict_step is forward(img).squeeze(1) (regression.py:338-339)")
+        img = self._check_img(img)
+        if self.training:
+            raise RuntimeError("instageo_b200.PrithviSeg is inference-only: call model.eval() first")
+        if not img.is_cuda:
+            raise RuntimeError("PrithviSeg.predict_proba needs a CUDA tensor: there is no CPU path")
+        dev, B, S = img.device, img.shape[0], self.image_size
+        self._sync_engine(dev)
+        ws = self._workspace(B, dev)
+        prob = torch.empty((B, S, S), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ig_model_predict_proba(self._engine, img.data_ptr(), _lib.IG_F32, B,
+                                                          prob.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                          _lib.current_stream()))
+        return prob
+
+    @torch.no_grad()
     def forward_patches(self, patches: torch.Tensor, want_logits: bool = True, want_argmax: bool = False):
         """Production entry: tubelet rows written by the fused preprocessing kernel
         (``ops.preprocess(..., want_patches=True)``), bf16 [B*T*196, 1536]."""

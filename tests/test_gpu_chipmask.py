@@ -62,6 +62,28 @@ def test_apply_mask_and_label_mask_alone(cuda_dev):
     assert mask_segmentation_map(c, s, -9).cpu().tolist() == [[-1, -1, -1, -1]]
 
 
+@pytest.mark.parametrize("dtype,no_data,clip", [(np.int16, -9999, (0, 10000)), (np.int16, 0, None), (np.int16, -9999, None),
+                                                (np.uint16, 0, (0, 65535)), (np.uint16, 65535, (100, 60000)),
+                                                (np.int16, 40000, (0, 65535)), (np.int16, 7, (5, 9)),
+                                                (np.uint16, 70000, (0, 10000)), (np.int16, -5, (40000, 50000))])
+def test_fill_value_and_clip_corner_cases(cuda_dev, dtype, no_data, clip):
+    """full-range inputs, fill values outside the clip range / the element type: the packed 16-bit path and the
+    scalar path it falls back to must both follow the integer arithmetic of the oracle."""
+    from instageo_b200.data import create_chip
+    rng = np.random.default_rng(abs(no_data) + 1)
+    info = np.iinfo(dtype)
+    chip = rng.integers(info.min, info.max + 1, size=(12, 40, 48)).astype(dtype)
+    chip[rng.random(chip.shape) < 0.05] = np.clip(no_data, info.min, info.max)
+    fmask = (rng.random((2, 40, 48)) < 0.3).astype(np.uint8) * 8
+    seg = rng.integers(-1, 3, size=(40, 48)).astype(np.int8)
+    for strategy in ("each", "any"):
+        out, seg_out, counts = create_chip(chip, fmask, seg, strategy, no_data_value=no_data, clip=clip)
+        want, want_seg, n_valid, n_lab = OP.create_chip(chip, fmask, seg, strategy, no_data_value=no_data, clip=clip)
+        got = out.cpu().numpy()
+        assert np.array_equal(got.astype(np.uint16), want.astype(np.uint16))  # compare 16-bit patterns
+        assert np.array_equal(seg_out.cpu().numpy(), want_seg) and counts.tolist() == [n_valid, n_lab]
+
+
 def test_whole_tile_properties(cuda_dev):
     """3660 x 3660 x 6 tile (BASELINE configs[3] geometry): idempotence and count consistency."""
     from instageo_b200.data import create_chip

@@ -135,3 +135,29 @@ def test_chip_inference_loop(cuda_dev, tmp_path):
         top2 = ref[i].topk(2, dim=0).values
         safe = ((top2[0] - top2[1]) > 1e-2).numpy()
         assert (p == ref[i].argmax(0).numpy())[safe].all()
+
+
+@pytest.mark.parametrize("T,nc", [(1, 2), (3, 13)])
+def test_predict_step_probability_and_regression_head(cuda_dev, T, nc):
+    """predict_step variants: softmax(logits)[:, 1] fused into the head epilogue
+    (segmentation.py:202-213) and the 1-channel regression head's forward().squeeze(1) (regression.py:338-339)."""
+    from oracle import metrics as OM
+    m, sd = _build("prithvi_eo_tiny", T, nc, 2, cuda_dev)
+    x = model_input(11, 2, T)
+    ref = P.prithvi_seg_forward(x, sd, P.VARIANTS["prithvi_eo_tiny"][2], T)
+    want = OM.positive_probability(ref)
+    got = m.predict_proba(x.to(cuda_dev)).cpu()
+    assert got.shape == want.shape and got.dtype == torch.float32
+    # |d softmax / d logit| <= 1/4 per logit, so a 2e-2 logit budget gives at most 1e-2 on a probability
+    assert (got - want).abs().max().item() < 1e-2
+    # the same epilogue without the logits round trip: identical to softmax of the engine's own logits to 2 ulp
+    own = torch.softmax(m(x.to(cuda_dev)), dim=1)[:, 1].cpu()
+    assert (got - own).abs().max().item() < 1e-6
+    if T == 1:
+        r, sdr = _build("prithvi_eo_tiny", 1, 1, 2, cuda_dev)
+        yr = r(x.to(cuda_dev))
+        assert yr.shape == (2, 1, 224, 224)
+        refr = P.prithvi_seg_forward(x, sdr, P.VARIANTS["prithvi_eo_tiny"][2], 1)
+        assert (yr.cpu() - refr).abs().max().item() < TOL
+        with pytest.raises(RuntimeError, match="classification head"):
+            r.predict_proba(x.to(cuda_dev))

@@ -253,10 +253,49 @@ def probe_bench():
         RES[f"bench_{variant}_T{T}_B{B}"] = B / ms * 1e3
 
 
+def probe_aux():
+    """§8(f) kernels: eval metrics and tile-scale chip masking -- time and achieved HBM bandwidth."""
+    from instageo_b200.data import create_chip
+    from instageo_b200.model.metrics import RunningAUC, RunningConfusionMatrix, segmentation_eval_update
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    g = torch.Generator(device="cuda").manual_seed(1042)
+    for nc, B, sharp in ((2, 64, 3.0), (13, 64, 3.0), (13, 64, 30.0)):  # sharp = 30: confident model, scores pile up in bins 0 / 1023
+        logits = torch.randn(B, nc, 224, 224, generator=g, device=dev) * sharp
+        labels = torch.randint(0, nc, (B, 224, 224), generator=g, device=dev)
+        labels[torch.rand(B, 224, 224, generator=g, device=dev) < 0.1] = -100
+        pred = logits.argmax(1).to(torch.int8)
+        cm, auc = RunningConfusionMatrix(nc, -100, device=dev), RunningAUC(nc, device=dev)
+        npx = B * 224 * 224
+        for name, fn, nbytes in (
+                ("confusion_from_int8_map", lambda: cm.update(labels, pred), npx * 9),
+                ("eval_step_confusion", lambda: segmentation_eval_update(logits, labels, cm, None), npx * (4 * nc + 8)),
+                ("eval_step_confusion_auc", lambda: segmentation_eval_update(logits, labels, cm, auc), npx * (4 * nc + 8))):
+            ms = timeit(fn)
+            RES[f"aux_{name}_nc{nc}_x{sharp:g}"] = dict(ms=ms, gbs=nbytes / ms / 1e6, frac_hbm=nbytes / ms / 1e6 / peak)
+            print(f"[{name} nc={nc} B={B} x{sharp:g}] {ms*1e3:.1f} us  {nbytes/ms/1e6:.0f} GB/s = {nbytes/ms/1e6/peak:.2f} of HBM peak")
+        # what the reference does per step with the same tensors (device part only; then 3 D2H copies + numpy)
+        def ref_step():
+            keep = labels.ne(-100).reshape(-1).nonzero().squeeze()
+            p_ = torch.argmax(logits, 1).reshape(-1)[keep]
+            q_ = torch.softmax(logits, 1).permute(0, 2, 3, 1).reshape(-1, nc)[keep]
+            return p_.cpu(), q_.cpu(), labels.reshape(-1)[keep].cpu()
+        ms = timeit(ref_step, iters=5)
+        RES[f"aux_reference_device_part_nc{nc}"] = dict(ms=ms)
+        print(f"[reference _shared_step gather + D2H, nc={nc}] {ms:.2f} ms (before its numpy bincount / add.at)")
+    for T in (1, 3):
+        tile = torch.randint(-100, 10200, (6 * T, 3660, 3660), generator=g, device=dev, dtype=torch.int16)
+        fm = (torch.rand((T, 3660, 3660), generator=g, device=dev) < 0.2).to(torch.uint8) * 2
+        seg = torch.randint(-1, 5, (3660, 3660), generator=g, device=dev, dtype=torch.int8)
+        nbytes = 3660 * 3660 * (6 * T * 4 + T + 2)
+        ms = timeit(lambda: create_chip(tile, fm, seg, "each"))
+        RES[f"aux_chip_mask_T{T}"] = dict(ms=ms, gbs=nbytes / ms / 1e6, frac_hbm=nbytes / ms / 1e6 / peak)
+        print(f"[chip_mask 3660^2 T={T}] {ms*1e3:.1f} us  {nbytes/ms/1e6:.0f} GB/s = {nbytes/ms/1e6/peak:.2f} of HBM peak")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     fams = dict(gemm=probe_gemm, ln=probe_ln, attn=probe_attn, pre=probe_pre, stitch=probe_stitch,
-                model=probe_model, perf=probe_perf, bench=probe_bench)
+                model=probe_model, perf=probe_perf, bench=probe_bench, aux=probe_aux)
     t0 = time.time()
     try:
         for k, f in fams.items():
