@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 
 VARIANT, T, NC, BATCH = "prithvi_eo_v1_100", 3, 13, 64
 # --workload: the default is BASELINE.json configs[1] (the bench line the driver records); the others are
-# extra measurements of configs[2] and configs[3] with the same JSON schema (profiles/r01_bench_*.json).
+# extra measurements of configs[2], configs[3] (tile_3660) and configs[4] (chipset_100k) with the same JSON schema
+# (profiles/r01_bench_*.json).
 WORKLOADS = {
     "chips_v1_100m_t3": ("prithvi_eo_v1_100", 3, 13, 64),
     "chips_v2_300m_t3": ("prithvi_eo_v2_300", 3, 13, 128),
@@ -243,18 +244,163 @@ def run_tile(args):
         dist.destroy_process_group()
 
 
+def run_chipset(args):
+    """BASELINE.json configs[4]: a large chip set (100 000 chips of 6 bands x 3 timesteps at 8 GPUs = 12 500 per GPU,
+    22.6 GB of int16 resident in each GPU's HBM) through fused normalise/mask -> Prithvi-V2-300M -> argmax, rank r
+    owning the contiguous chip block partition(n, world, r), then ONE NCCL all-gather of the int8 masks into dataset
+    order.  One step = one pass over the whole set; value = chips/s over all ranks (weak scaling: 12 500 chips/GPU)."""
+    import torch
+    import torch.distributed as dist
+
+    import instageo_b200
+    from instageo_b200 import _lib, ops
+    from instageo_b200.model import PrithviSeg
+    from instageo_b200.model import infer_utils as IU
+    from instageo_b200.model.model import flops_per_chip
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    variant, t, nc, batch = "prithvi_eo_v2_300", 3, 13, 128
+    n_total = args.chips if args.chips else 12500 * world
+    lo, hi = IU.partition(n_total, world, rank)
+    n_local = hi - lo
+    torch.manual_seed(0)
+    model = PrithviSeg(temporal_step=t, num_classes=nc, load_pretrained_weights=False, variant=variant).to(dev).eval()
+    spec = ops.PreprocessSpec(CROP_MEAN, CROP_STD, t, None, 1.0, None, dev)
+    # the shard is generated on the device, chunk by chunk, from a seed per chunk's first chip index
+    d_raw = torch.empty((n_local, t * 6, 224, 224), dtype=torch.int16, device=dev)
+    for c0 in range(0, n_local, 500):
+        g = torch.Generator(device=dev).manual_seed(1042 + lo + c0)
+        c1 = min(n_local, c0 + 500)
+        d_raw[c0:c1] = torch.randint(0, 10001, (c1 - c0, t * 6, 224, 224), generator=g, dtype=torch.int16, device=dev)
+    masks = torch.empty((n_local, 224, 224), dtype=torch.int8, device=dev)
+
+    def one_batch(i):
+        pre = ops.preprocess(d_raw[i:i + batch], spec, want_f32=False, want_patches=True)
+        masks[i:i + batch] = model.forward_patches(pre["patches"], want_logits=False, want_argmax=True)[1]
+
+    def step():
+        for i in range(0, n_local, batch):
+            one_batch(i)
+        return IU.gather_chip_masks(masks, n_total, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):          # warm-up: macro-batches, not whole passes (a pass is ~8 s)
+        one_batch((i * batch) % max(1, n_local - batch))
+    if world > 1:
+        IU.gather_chip_masks(masks, n_total, world)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        full = step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    clocks = sampler.stop() if rank == 0 else None
+    assert full.shape[0] == n_total
+    # gather alone (the only collective of the path)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record()
+    IU.gather_chip_masks(masks, n_total, world)
+    g1.record()
+    barrier()
+    gather_ms = g0.elapsed_time(g1)
+    del full
+    # roofline of the GEMM family over 8 instrumented macro-batches
+    n_prof = min(8, max(1, n_local // batch))
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    for i in range(n_prof):
+        one_batch(i * batch)
+    torch.cuda.synchronize()
+    fam = _lib.profile_report()
+    _lib.profile_enable(False)
+    enc = model.prithvi_encoder
+    fl = flops_per_chip(enc.embed_dim, len(enc.blocks), t, nc)
+    n_tok = t * 196 + 1
+    gemm_fl = (fl["total"] - len(enc.blocks) * 4 * n_tok * n_tok * enc.embed_dim) * batch * n_prof
+    gemm_ms = fam["gemm_linear"][0] + fam["gemm_conv"][0]
+    gemm_n = fam["gemm_linear"][1] + fam["gemm_conv"][1]
+    peak_tf, peak_gbs, peak_src = peaks()
+    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else 0.0
+    all_ms = sum(v[0] for v in fam.values())
+    # end to end: the same number of macro-batches streamed from pinned HOST memory (4 rotating host batches --
+    # pinning the whole 22.6 GB shard per rank would only measure the allocator), masks back on the host
+    pipe = IU.ChipPipeline(model, spec, batch, dev)
+    g = torch.Generator().manual_seed(7 + rank)
+    pinned = [torch.randint(0, 10001, (batch, t * 6, 224, 224), generator=g, dtype=torch.int16).pin_memory() for _ in range(4)]
+    n_b = (n_local + batch - 1) // batch
+    sink = []
+    pipe.run([pinned[i % 4] for i in range(3)], consume=lambda a: None)
+    barrier()
+    t0 = time.perf_counter()
+    pipe.run([pinned[i % 4] for i in range(n_b)], consume=lambda a: sink.append(int(a[0, 0, 0])))
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out = {"metric": METRIC, "value": n_total * args.steps / (ms / 1e3), "unit": "chips/s", "n_gpus": world,
+           "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"chipset_{n_total}_chips_prithvi_v2_300m_T3_nc13: resident int16 shard -> normalise/mask -> "
+                                  "PrithviSeg -> argmax int8 -> NCCL all-gather of the masks",
+                      "chips_per_gpu": n_local, "shard_bytes": n_local * t * 6 * 224 * 224 * 2, "macro_batch": batch,
+                      "parallelism": f"contiguous chip blocks x{world}, one int8 all-gather per pass",
+                      "warmup_unit": "macro-batches of 128 chips (one pass is one step)",
+                      "l2": "22.6 GB shard streamed once per pass, far larger than L2"},
+           "clocks": clocks,
+           "e2e": {"value": world * n_b * batch / dt.item(), "unit": "chips/s", "h2d_bytes_per_step": pipe.h2d_bytes * n_b,
+                   "d2h_bytes_per_step": pipe.d2h_bytes * n_b,
+                   "api": "instageo_b200.model.infer_utils.ChipPipeline.run over the shard's macro-batches (pinned host int16 in, int8 masks out)"},
+           "gpu_launches": (model.launches_per_forward()) * n_b * args.steps,
+           "gather": {"ms": gather_ms, "bytes_out_per_rank": n_total * 224 * 224,
+                      "gbs_per_rank": n_total * 224 * 224 / (gather_ms / 1e3) / 1e9 if world > 1 else None},
+           "roofline": {"kernel": "gemm_kernel<EPI> (tcgen05 GEMM: encoder linears + head implicit-GEMM convs)", "bound": "tensor",
+                        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                        "peak_source": peak_src, "avg_launch_ms": gemm_ms / max(1, gemm_n),
+                        "share_of_step": gemm_ms / all_ms if all_ms else None,
+                        "timing": f"cuda events around every launch of {n_prof} macro-batches after the timed region"},
+           "kernel_families": {k: {"ms_per_batch": v[0] / n_prof, "launches_per_batch": v[1] / n_prof} for k, v in fam.items()}}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default 20 (chipset_100k: 1 pass)")
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--chips", type=int, default=0, help="chipset_100k: total chips (default 12500 per GPU)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="chips_v1_100m_t3", choices=sorted(WORKLOADS) + ["tile_3660"])
+    ap.add_argument("--workload", default="chips_v1_100m_t3", choices=sorted(WORKLOADS) + ["tile_3660", "chipset_100k"])
     ap.add_argument("--stride", type=int, default=224, help="tile_3660: sliding-window stride")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1 if args.workload == "chipset_100k" else 20
     if args.workload == "tile_3660":
         return run_tile(args)
+    if args.workload == "chipset_100k":
+        return run_chipset(args)
     global VARIANT, T, NC, BATCH, WORKLOAD
     VARIANT, T, NC, BATCH = WORKLOADS[args.workload]
     if args.workload != "chips_v1_100m_t3":
