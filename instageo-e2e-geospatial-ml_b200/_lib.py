@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libinstageo_b200.so")
+# INSTAGEO_B200_LIB: developer override used by the timing-ablation tooling (tools/attn_ablate.sh)
+LIB_PATH = os.environ.get("INSTAGEO_B200_LIB") or os.path.join(HERE, "libinstageo_b200.so")
 
 IG_F32, IG_BF16, IG_I16, IG_U16, IG_F64 = 0, 1, 2, 3, 4
 IG_I64, IG_I32, IG_U8, IG_I8 = 5, 6, 7, 8

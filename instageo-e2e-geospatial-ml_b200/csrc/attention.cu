@@ -42,6 +42,29 @@ constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_O = 128, COL_L = 192;  // S buffers at 0 / 64, O at 128..191, L at 192..199
 constexpr float RESCALE_LOG2 = 8.f;                 // raise the reference max only for jumps > 2^8
+// Timing ablations (tools/attn_ablate.sh; never defined in the shipped library): 1 = no MUFU (exp2 -> identity),
+// 2 = no P stores, 3 = no TMEM loads of S, 4 = no max pass, 5 / 6 / 7 = one instead of four L / PV / QK UMMAs per
+// KV block.  Results are wrong by construction.
+#ifndef ATTN_ABLATE
+#define ATTN_ABLATE 0
+#endif
+// In-kernel phase timing (-DATTN_PROFILE, tools/attn_ablate.sh): clock64 deltas of lane 0 of softmax warp 2 and of
+// the MMA warp, summed over all CTAs into g_attn_prof[16]; read back through ig_attention_profile().
+#ifdef ATTN_PROFILE
+__device__ unsigned long long g_attn_prof[16];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, t0, t1) do { if (lane == 0 && (warp == 2 || warp == 1)) atomicAdd(&g_attn_prof[slot], static_cast<unsigned long long>((t1) - (t0))); } while (0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, t0, t1)
+#endif
+__device__ __forceinline__ float exp2_or_ablate(float x) {
+#if ATTN_ABLATE == 1
+  return x;
+#else
+  return ig::ex2(x);
+#endif
+}
 static_assert(OFF_ONES % 1024 == 0, "UMMA operand tiles are 1024-byte aligned");
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -65,6 +88,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
+  PROF_T(cta0);
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nb = (N + BKV - 1) / BKV;
   const int row0 = b * N;  // first token row of this batch element in the qkv matrix
@@ -120,25 +144,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
+    // Descriptors are formed ADDITIVELY from five base words computed once (start address >> 4 in the low
+    // word; a stage / buffer / K-step is a constant added to it), so a UMMA costs one or two uniform-datapath
+    // adds instead of a shift-mask-or chain per operand: the single issuing warp is a serial instruction stream
+    // and was the slowest actor of the CTA (in-kernel clock64 profile: ~700 clk to issue PV_j, ~900 for QK_{j+2},
+    // while the softmax warps waited ~1200 clk per block for S_j).
     const uint32_t idesc = ig::umma_idesc_bf16(BQ, BKV, 0, 0);    // S = Q K^T (N = 64 kv)
     const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O += P V  (B = V, MN-major)
     const uint32_t idesc_l = ig::umma_idesc_bf16(BQ, 8, 0, 0);    // L += P 1  (B = ones, K-major, N = 8)
-    const uint32_t sq = ig::smem_u32(smem + OFF_Q);
-    const uint32_t sk = ig::smem_u32(smem + OFF_K);
-    const uint32_t sv = ig::smem_u32(smem + OFF_V);
-    const uint32_t sp = ig::smem_u32(smem + OFF_P);
-    const uint32_t so = ig::smem_u32(smem + OFF_ONES);
+    const uint32_t smem_base = ig::smem_u32(smem);
+    const uint32_t q_lo = ig::umma_desc_lo(smem_base + OFF_Q);        // K-major tiles: LBO 16, SBO 1024
+    const uint32_t k_lo = ig::umma_desc_lo(smem_base + OFF_K);
+    const uint32_t p_lo = ig::umma_desc_lo(smem_base + OFF_P);
+    const uint32_t one_lo = ig::umma_desc_lo(smem_base + OFF_ONES);
+    // V is consumed MN-major straight from its [kv, 64] tile: 16 kv rows of 128 bytes per K step, 8-row groups
+    // 1024 B apart (LBO = SBO = 1024)
+    const uint32_t v_lo = (((smem_base + OFF_V) & 0x3FFFF) >> 4) | ((1024u >> 4) << 16);
     auto issue_qk = [&](int i) {
       const int st = i % KV_STAGES, sb = i & 1;
       ig::mbar_wait(&k_full[st], (i / KV_STAGES) & 1);
       ig::mbar_wait(&s_free[sb], ((i >> 1) & 1) ^ 1);
       ig::tc_fence_after();
+      const uint32_t dk = k_lo + st * (KV_BYTES >> 4);
+      const uint32_t d_s = tmem_base + COL_S + sb * BKV;
       if (ig::elect_one()) {
-        const uint64_t dq = ig::umma_desc_sw128(sq, 1024, 16);
-        const uint64_t dk = ig::umma_desc_sw128(sk + st * KV_BYTES, 1024, 16);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ig::umma_bf16(tmem_base + COL_S + sb * BKV, dq + 2 * k, dk + 2 * k, idesc, k > 0);
+        for (int k = 0; k < (ATTN_ABLATE == 7 ? 1 : HD / 16); ++k)
+          ig::umma_bf16(d_s, ig::umma_desc_pack(q_lo + 2 * k), ig::umma_desc_pack(dk + 2 * k), idesc, k > 0);
         ig::umma_commit(&s_full[sb]);
         ig::umma_commit(&k_empty[st]);
       }
@@ -149,26 +181,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     if (nb > 1) issue_qk(1);
     for (int j = 0; j < nb; ++j) {
       const int st = j % KV_STAGES, pb = j & 1;
+      // S_{j+2} = Q K_{j+2}^T goes first: it needs only the S buffer that the softmax warps hand back as soon as
+      // S_j is in their registers, not P_j -- so the scores of the next two blocks are always ready ahead of the
+      // softmax warps and the QK issue latency is off the P_j -> PV_j critical path.
+      PROF_T(m0);
+      if (j + 2 < nb) issue_qk(j + 2);
+      PROF_T(m1);
       ig::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
       ig::mbar_wait(&p_full[pb], (j >> 1) & 1);  // P_j is in smem and any rescale of O / L is finished
+      PROF_T(m2);
       ig::tc_fence_after();
+      const uint32_t dp = p_lo + pb * (P_BYTES >> 4);
+      const uint32_t dv = v_lo + st * (KV_BYTES >> 4);
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
       if (ig::elect_one()) {
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           // A = P_j: 128 rows x 64 kv (one swizzle atom column), 32 bytes per K step
-          const uint64_t dp = ig::umma_desc_sw128(sp + pb * P_BYTES + k * 32, 1024, 16);
-          // B = V_j (MN-major): 16 kv rows of 128 bytes per K step, 8-row groups 1024 B apart
-          const uint64_t dv = ig::umma_desc_sw128(sv + st * KV_BYTES + k * 2048, 1024, 1024);
-          ig::umma_bf16(tmem_base + COL_O, dp, dv, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          const uint64_t d1 = ig::umma_desc_sw128(so + k * 32, 1024, 16);
-          ig::umma_bf16(tmem_base + COL_L, dp, d1, idesc_l, (j > 0 || k > 0) ? 1u : 0u);
+          const uint64_t da = ig::umma_desc_pack(dp + 2 * k);
+          if (ATTN_ABLATE != 6 || k == 0)
+            ig::umma_bf16(tmem_base + COL_O, da, ig::umma_desc_pack(dv + k * (2048 >> 4)), idesc_o, k > 0 ? 1u : acc0);
+          if (ATTN_ABLATE != 5 || k == 0)
+            ig::umma_bf16(tmem_base + COL_L, da, ig::umma_desc_pack(one_lo + 2 * k), idesc_l, k > 0 ? 1u : acc0);
         }
         ig::umma_commit(&o_done[pb]);
         ig::umma_commit(&v_empty[st]);
         ig::umma_commit(&p_free[pb]);
       }
       __syncwarp();
-      if (j + 2 < nb) issue_qk(j + 2);
+      PROF_T(m3);
+      PROF_ADD(8, m0, m1);   // issue QK_{j+2} (incl. waits K, S free)
+      PROF_ADD(9, m1, m2);   // wait V_j, P_j
+      PROF_ADD(10, m2, m3);  // issue PV_j
     }
   } else {
     // ===================== softmax / output warps (one thread per query row) =====================
@@ -187,15 +231,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     for (int j = 0; j < nb; ++j) {
       const int kv0 = j * BKV, sb = j & 1;
       const int nvalid = min(BKV, N - kv0);  // warp-uniform
+      PROF_T(c0);
       ig::mbar_wait(&s_full[sb], (j >> 1) & 1);
+      PROF_T(c1);
       ig::tc_fence_after();
+#if ATTN_ABLATE == 3
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sc[i] = __float_as_uint(0.01f * (i + j + lane));
+#else
       ig::tmem_ld32(t_s + sb * BKV, sa);
       ig::tmem_ld32(t_s + sb * BKV + 32, sb2);
       ig::tmem_ld_wait();
+#endif
       // the scores are in registers: hand the S buffer back so QK^T of block j+2 can start
       ig::tc_fence_before();
       __syncwarp();
       if (lane == 0) ig::mbar_arrive(&s_free[sb]);
+      PROF_T(c2);
       if (nvalid < BKV) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -209,7 +261,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
         mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sc[i + 4]), __uint_as_float(sc[i + 5])));
         mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sc[i + 6]), __uint_as_float(sc[i + 7])));
       }
+#if ATTN_ABLATE == 4
+      const float m_blk = __uint_as_float(sc[lane & 63]);
+#else
       const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+#endif
       if (j == 0) {
         m_ref = m_blk;
       } else {
@@ -239,7 +295,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       }
       const float mc = m_ref * sl2;
       // ---- exponentials -> P_j (bf16, swizzled smem); fully masked 16-column groups are written as zeros
+      PROF_T(c3);
       ig::mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
+      PROF_T(c4);
       uint8_t* prow = smem + OFF_P + sb * P_BYTES + row * 128;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -247,14 +305,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
         if (g * 16 < nvalid) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float p0 = ig::ex2(fmaf(__uint_as_float(sc[g * 16 + 2 * i]), sl2, -mc));
-            const float p1 = ig::ex2(fmaf(__uint_as_float(sc[g * 16 + 2 * i + 1]), sl2, -mc));
+            const float p0 = exp2_or_ablate(fmaf(__uint_as_float(sc[g * 16 + 2 * i]), sl2, -mc));
+            const float p1 = exp2_or_ablate(fmaf(__uint_as_float(sc[g * 16 + 2 * i + 1]), sl2, -mc));
             pk[i] = ig::pack_bf16(p0, p1);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = 0u;
         }
+#if ATTN_ABLATE == 2
+        if (pk[0] == 0x12345678u)
+#endif
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int chunk = g * 2 + q;  // 16-byte chunk inside the 128-byte row
@@ -262,13 +323,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
+      PROF_T(c5);
       ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
       ig::tc_fence_before();         // orders a rescale's tcgen05.st before the MMA warp's PV_j
       __syncwarp();
       if (lane == 0) ig::mbar_arrive(&p_full[sb]);
+      PROF_T(c6);
+      if (j == 0) { PROF_ADD(6, c0, c1); PROF_ADD(12, cta0, c0); }  // first block: wait S_0; kernel start -> softmax loop
+      PROF_ADD(0, c0, c1);  // wait S_j
+      PROF_ADD(1, c1, c2);  // TMEM load of S_j
+      PROF_ADD(2, c2, c3);  // mask + max (+ rescale)
+      PROF_ADD(3, c3, c4);  // wait P buffer free
+      PROF_ADD(4, c4, c5);  // exponentials + P stores
+      PROF_ADD(5, c5, c6);  // fences + arrive
     }
     // ---- epilogue: O / L
+    PROF_T(e0);
     ig::mbar_wait(&o_done[(nb - 1) & 1], ((nb - 1) >> 1) & 1);
+    PROF_T(e1);
+    PROF_ADD(7, e0, e1);  // wait for the last PV
     ig::tc_fence_after();
     ig::tmem_ld32(t_o, sa);
     ig::tmem_ld32(t_o + 32, sb2);
@@ -288,6 +361,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
         reinterpret_cast<uint4*>(orow)[q] = o;
       }
     }
+#ifdef ATTN_PROFILE
+    { PROF_T(e2); PROF_ADD(13, e1, e2); }  // O load, normalise, store
+#endif
   }
 
   ig::tc_fence_before();
@@ -296,9 +372,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     ig::tc_fence_after();
     ig::tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#ifdef ATTN_PROFILE
+  {
+    PROF_T(cta1);
+    if (threadIdx.x == 64) {
+      atomicAdd(&g_attn_prof[14], static_cast<unsigned long long>(cta1 - cta0));
+      atomicAdd(&g_attn_prof[15], 1ull);
+    }
+  }
+#endif
 }
 
 }  // namespace attn
+
+#ifdef ATTN_PROFILE
+extern "C" int ig_attention_profile(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, attn::g_attn_prof, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(attn::g_attn_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 namespace ops {
 int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t st) {
