@@ -29,11 +29,12 @@ namespace attn {
 constexpr int BQ = 128, BKV = 64, HD = 64;
 constexpr int Q_BYTES = BQ * HD * 2;    // 16384
 constexpr int KV_BYTES = BKV * HD * 2;  // 8192
-constexpr int KV_STAGES = 3;
-constexpr int OFF_Q = 0;
+constexpr int K_STAGES = 4, V_STAGES = 3;
+constexpr int L2_AHEAD = 6;  // KV blocks between a tile's L2 prefetch and its TMA load
+constexpr int OFF_Q = 0;                              // [128 x 64] bf16
 constexpr int OFF_K = OFF_Q + Q_BYTES;
-constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
-constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;  // 2 x [128 x 64] bf16 (one swizzle atom column each)
+constexpr int OFF_V = OFF_K + K_STAGES * KV_BYTES;
+constexpr int OFF_P = OFF_V + V_STAGES * KV_BYTES;   // 2 x [128 x 64] bf16 (one swizzle atom column each)
 constexpr int P_BYTES = BQ * BKV * 2;                 // 16384
 constexpr int OFF_ONES = OFF_P + 2 * P_BYTES;         // [8 x 64] bf16 ones (K-major B operand of the L MMA)
 constexpr int OFF_BAR = OFF_ONES + 1024;
@@ -42,21 +43,39 @@ constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_O = 128, COL_L = 192;  // S buffers at 0 / 64, O at 128..191, L at 192..199
 constexpr float RESCALE_LOG2 = 8.f;                 // raise the reference max only for jumps > 2^8
+static_assert(OFF_ONES % 1024 == 0 && OFF_K % 1024 == 0, "UMMA operand tiles are 1024-byte aligned");
+static_assert(2 * SMEM_TOTAL <= 232448 - 2048, "two CTAs per SM");
 // Timing ablations (tools/attn_ablate.sh; never defined in the shipped library): 1 = no MUFU (exp2 -> identity),
-// 2 = no P stores, 3 = no TMEM loads of S, 4 = no max pass, 5 / 6 / 7 = one instead of four L / PV / QK UMMAs per
-// KV block.  Results are wrong by construction.
+// 2 = no P stores, 5 / 6 / 7 = one instead of four L / PV / QK UMMAs per KV block.  Results are wrong by construction.
 #ifndef ATTN_ABLATE
 #define ATTN_ABLATE 0
 #endif
 // In-kernel phase timing (-DATTN_PROFILE, tools/attn_ablate.sh): clock64 deltas of lane 0 of softmax warp 2 and of
 // the MMA warp, summed over all CTAs into g_attn_prof[16]; read back through ig_attention_profile().
 #ifdef ATTN_PROFILE
-__device__ unsigned long long g_attn_prof[16];
+__device__ unsigned long long g_attn_prof[32];
+// event trace of CTA 0 (ATTN_PROFILE == 3): [role 0 producer | 1 mma | 2 softmax warp 2][4096] x {event, block, clock}
+__device__ long long g_attn_trace[3][4096][3];
+__device__ int g_attn_trace_n[3];
+__device__ __forceinline__ void attn_trace(int role, int ev, int blk) {
+#if ATTN_PROFILE == 3
+  if (blockIdx.x == 0) {
+    const int i = atomicAdd(&g_attn_trace_n[role], 1);
+    if (i < 4096) {
+      g_attn_trace[role][i][0] = ev;
+      g_attn_trace[role][i][1] = blk;
+      g_attn_trace[role][i][2] = clock64();
+    }
+  }
+#endif
+}
+#define TRACE(role, ev, blk) do { if (lane == 0 || (role) == 0) attn_trace(role, ev, blk); } while (0)
 #define PROF_T(var) const long long var = clock64()
-#define PROF_ADD(slot, t0, t1) do { if (lane == 0 && (warp == 2 || warp == 1)) atomicAdd(&g_attn_prof[slot], static_cast<unsigned long long>((t1) - (t0))); } while (0)
+#define PROF_ADD(slot, t0, t1) do { if (lane == 0 && warp <= 2) atomicAdd(&g_attn_prof[slot], static_cast<unsigned long long>((t1) - (t0))); } while (0)
 #else
 #define PROF_T(var)
 #define PROF_ADD(slot, t0, t1)
+#define TRACE(role, ev, blk)
 #endif
 __device__ __forceinline__ float exp2_or_ablate(float x) {
 #if ATTN_ABLATE == 1
@@ -65,44 +84,46 @@ __device__ __forceinline__ float exp2_or_ablate(float x) {
   return ig::ex2(x);
 #endif
 }
-static_assert(OFF_ONES % 1024 == 0, "UMMA operand tiles are 1024-byte aligned");
 
+// PERSISTENT kernel: gridDim.x = min(work items, 2 x SMs) CTAs, each walks work items w = blockIdx.x, +gridDim.x, ...
+// (one item = 128 query rows of one (batch, head), query tile fastest).  All rings and double buffers run on a
+// KV-block counter that keeps counting across items, so the TMA producer and the QK^T issue run ahead INTO THE
+// NEXT ITEM while the softmax warps finish the current one.  The first version launched one short-lived CTA per
+// item and spent 28 % of every CTA's life outside the steady state (in-kernel clock64 profile, per CTA of ~33.6 k
+// clk: 5.1 k waiting for the first S tile behind the Q / K_0 loads, 1.4 k for the last PV, 2.0 k in the output
+// epilogue, 0.85 k of set-up), with TMEM allocated and freed 3840 times per launch.
 __global__ void __launch_bounds__(THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
-                 __nv_bfloat16* __restrict__ out, int N, int D) {
+                 __nv_bfloat16* __restrict__ out, int N, int D, int nqt, int heads, int total_items) {
   extern __shared__ uint8_t smem_raw[];
   // offset arithmetic on the __shared__ array itself (not a round trip through uintptr_t) keeps the pointer in
   // the shared address space: LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math
   uint8_t* smem = smem_raw + ((1024u - (ig::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [3]
-  uint64_t* k_empty = bars + 4;   // [3]
-  uint64_t* v_full = bars + 7;    // [3]
-  uint64_t* v_empty = bars + 10;  // [3]
-  uint64_t* s_full = bars + 13;   // [2]
-  uint64_t* s_free = bars + 15;   // [2]
-  uint64_t* p_full = bars + 17;   // [2]
-  uint64_t* p_free = bars + 19;   // [2]
-  uint64_t* o_done = bars + 21;   // [2]  PV_j (and everything before it) has completed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 23);
+  uint64_t* q_full = bars + 0;    // [1]
+  uint64_t* q_empty = bars + 1;   // [1]  every QK^T of the item has completed
+  uint64_t* k_full = bars + 2;    // [4]
+  uint64_t* k_empty = bars + 6;   // [4]
+  uint64_t* v_full = bars + 10;   // [3]
+  uint64_t* v_empty = bars + 13;  // [3]
+  uint64_t* s_full = bars + 16;   // [2]
+  uint64_t* s_free = bars + 18;   // [2]
+  uint64_t* p_full = bars + 20;   // [2]
+  uint64_t* p_free = bars + 22;   // [2]
+  uint64_t* o_done = bars + 24;   // [2]  PV of a block (and everything before it) has completed
+  uint64_t* o_free = bars + 26;   // [1]  the softmax warps have read O / L of the finished item
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
   PROF_T(cta0);
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int nb = (N + BKV - 1) / BKV;
-  const int row0 = b * N;  // first token row of this batch element in the qkv matrix
+  const int items_per_bh = nqt;
 
   if (warp == 0 && lane == 0) {
     ig::tma_prefetch_desc(&tmq);
     ig::tma_prefetch_desc(&tmkv);
     ig::mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
-      ig::mbar_init(&k_full[s], 1);
-      ig::mbar_init(&k_empty[s], 1);
-      ig::mbar_init(&v_full[s], 1);
-      ig::mbar_init(&v_empty[s], 1);
-    }
+    ig::mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       ig::mbar_init(&s_full[s], 1);
       ig::mbar_init(&s_free[s], 4);
@@ -110,6 +131,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       ig::mbar_init(&p_free[s], 1);
       ig::mbar_init(&o_done[s], 1);
     }
+    for (int s = 0; s < K_STAGES; ++s) {
+      ig::mbar_init(&k_full[s], 1);
+      ig::mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < V_STAGES; ++s) {
+      ig::mbar_init(&v_full[s], 1);
+      ig::mbar_init(&v_empty[s], 1);
+    }
+    ig::mbar_init(o_free, 4);
     ig::fence_barrier_init();
   }
   if (warp == 1) {
@@ -126,78 +156,188 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   ig::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
+  // Both issuing warps need these (uniform values; descriptors are formed ADDITIVELY from base words computed
+  // once: start address >> 4 in the low word, a stage / buffer / K-step is a constant added to it, so a UMMA costs
+  // one or two uniform-datapath adds instead of a shift-mask-or chain per operand).
+  const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int total_blocks = my_items * nb;
+  const uint32_t smem_base = ig::smem_u32(smem);
+
   if (warp == 0) {
-    if (ig::elect_one()) {
-      // ===================== TMA producer =====================
-      ig::mbar_expect_tx(q_full, Q_BYTES);
-      ig::tma_load_2d(smem + OFF_Q, &tmq, q_full, h * HD, row0 + q0);
-      for (int j = 0; j < nb; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t par = ((j / KV_STAGES) & 1) ^ 1;
-        ig::mbar_wait(&k_empty[st], par);
-        ig::mbar_expect_tx(&k_full[st], KV_BYTES);
-        ig::tma_load_2d(smem + OFF_K + st * KV_BYTES, &tmkv, &k_full[st], D + h * HD, row0 + j * BKV);
-        ig::mbar_wait(&v_empty[st], par);
-        ig::mbar_expect_tx(&v_full[st], KV_BYTES);
-        ig::tma_load_2d(smem + OFF_V + st * KV_BYTES, &tmkv, &v_full[st], 2 * D + h * HD, row0 + j * BKV);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====
-    // Descriptors are formed ADDITIVELY from five base words computed once (start address >> 4 in the low
-    // word; a stage / buffer / K-step is a constant added to it), so a UMMA costs one or two uniform-datapath
-    // adds instead of a shift-mask-or chain per operand: the single issuing warp is a serial instruction stream
-    // and was the slowest actor of the CTA (in-kernel clock64 profile: ~700 clk to issue PV_j, ~900 for QK_{j+2},
-    // while the softmax warps waited ~1200 clk per block for S_j).
+    // ===================== warp 0: TMA producer + QK^T issuer =====================
+    // A single issuing warp is a serial instruction stream: with one warp issuing QK^T and PV (12 UMMAs, 5
+    // commits and 4 barrier waits per KV block, ~1300 clk) it, not the softmax warps, set the pace of the CTA
+    // (event trace of CTA 0, tools/attn_trace.py).  QK^T issue therefore lives here, next to the two TMA loads
+    // per block, and warp 1 issues only PV.
+    // Order per block g:  V_g load (buffer released by PV_{g-2})  ->  K_{g+3} load (+ the next item's Q in
+    // front of its first block; released by QK_g)  ->  S_{g+2} = Q K_{g+2}^T (S buffer handed back by the
+    // softmax warps as soon as S_g is in their registers).  K runs three blocks ahead of V, QK^T two blocks
+    // ahead of PV, across item boundaries.
     const uint32_t idesc = ig::umma_idesc_bf16(BQ, BKV, 0, 0);    // S = Q K^T (N = 64 kv)
-    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O += P V  (B = V, MN-major)
-    const uint32_t idesc_l = ig::umma_idesc_bf16(BQ, 8, 0, 0);    // L += P 1  (B = ones, K-major, N = 8)
-    const uint32_t smem_base = ig::smem_u32(smem);
     const uint32_t q_lo = ig::umma_desc_lo(smem_base + OFF_Q);        // K-major tiles: LBO 16, SBO 1024
     const uint32_t k_lo = ig::umma_desc_lo(smem_base + OFF_K);
+    // The issuing warps are single serial instruction streams (one dependent instruction every ~6 clk): all
+    // ring / parity / coordinate state is CARRIED and updated incrementally, an item is decoded (three integer
+    // divisions) once per item and not per block.  With divisions and modulos per block this warp needed ~3000 clk
+    // per KV block and was the slowest actor of the CTA (event trace, tools/attn_trace.py).
+    const int gstride = gridDim.x;
+    // K stream
+    int k_left = total_blocks, k_j = 0, k_w = blockIdx.x, k_st = 0, k_col = 0, k_row = 0;
+    uint32_t k_par = 1;  // parity to wait for on k_empty (fresh barrier: passes)
+    auto decode = [&](int w, int& col_h, int& row0, int& qrow) {
+      const int bh = w / items_per_bh, qt = w - bh * items_per_bh;
+      const int b = bh / heads, h = bh - b * heads;
+      col_h = h * HD, row0 = b * N, qrow = b * N + qt * BQ;
+    };
+    int dummy_q;
+    if (total_blocks > 0) {
+      int ch, r0;
+      decode(k_w, ch, r0, dummy_q);
+      k_col = D + ch, k_row = r0;
+      if (ig::elect_one()) {
+        ig::mbar_expect_tx(q_full, Q_BYTES);
+        ig::tma_load_2d(smem + OFF_Q, &tmq, q_full, ch, dummy_q);
+      }
+      __syncwarp();
+    }
+    auto emit_k = [&]() {
+      ig::mbar_wait(&k_empty[k_st], k_par);
+      if (ig::elect_one()) {
+        TRACE(0, 1, k_left);  // K load issued
+        ig::mbar_expect_tx(&k_full[k_st], KV_BYTES);
+        ig::tma_load_2d(smem + OFF_K + k_st * KV_BYTES, &tmkv, &k_full[k_st], k_col, k_row);
+      }
+      __syncwarp();
+      --k_left;
+      k_row += BKV;
+      if (++k_st == K_STAGES) k_st = 0, k_par ^= 1;
+      if (++k_j == nb) {
+        k_j = 0, k_w += gstride;
+        if (k_left > 0) {
+          int ch, r0;
+          decode(k_w, ch, r0, dummy_q);
+          k_col = D + ch, k_row = r0;
+        }
+      }
+    };
+    // QK^T stream
+    int q_left = total_blocks, q_j = 0, q_n = 0, q_st = 0, q_sb = 0;
+    uint32_t q_kpar = 0, q_spar = 1;  // parities to wait for on k_full / s_free
+    auto issue_qk = [&]() {
+      PROF_T(w0);
+      if (q_j == 0) ig::mbar_wait(q_full, q_n & 1);
+      ig::mbar_wait(&k_full[q_st], q_kpar);
+      PROF_T(w1);
+      ig::mbar_wait(&s_free[q_sb], q_spar);
+      PROF_T(w2);
+      TRACE(1, 10, q_left);    // QK waits satisfied
+      ig::tc_fence_after();
+      const uint32_t dk = k_lo + q_st * (KV_BYTES >> 4);
+      const uint32_t d_s = tmem_base + COL_S + q_sb * BKV;
+      const bool last = q_j == nb - 1;
+      if (ig::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < (ATTN_ABLATE == 7 ? 1 : HD / 16); ++k)
+          ig::umma_bf16(d_s, ig::umma_desc_pack(q_lo + 2 * k), ig::umma_desc_pack(dk + 2 * k), idesc, k > 0);
+        ig::umma_commit(&s_full[q_sb]);
+        ig::umma_commit(&k_empty[q_st]);
+        if (last) ig::umma_commit(q_empty);
+      }
+      __syncwarp();
+      PROF_T(w3);
+      PROF_ADD(11, w0, w1);  // QK: wait Q / K
+      PROF_ADD(6, w1, w2);   // QK: wait S buffer free
+      PROF_ADD(8, w2, w3);   // QK: issue
+      TRACE(1, 11, q_left);  // QK issued
+      --q_left;
+      if (++q_st == K_STAGES) q_st = 0, q_kpar ^= 1;
+      q_sb ^= 1;
+      if (q_sb == 0) q_spar ^= 1;
+      if (++q_j == nb) {
+        // The item's last QK^T is in flight: as soon as it has completed, the (single) Q tile is reloaded for
+        // the next item -- two blocks before that item's first QK^T is issued.
+        if (q_left > 0) {
+          int ch, r0, qrow;
+          decode(static_cast<int>(blockIdx.x) + (q_n + 1) * gstride, ch, r0, qrow);
+          ig::mbar_wait(q_empty, q_n & 1);
+          if (ig::elect_one()) {
+            ig::mbar_expect_tx(q_full, Q_BYTES);
+            ig::tma_load_2d(smem + OFF_Q, &tmq, q_full, ch, qrow);
+          }
+          __syncwarp();
+        }
+        q_j = 0, ++q_n;
+      }
+    };
+    // Per block g:  K_{g+4} load (buffer released by QK_g)  ->  S_{g+2} = Q K_{g+2}^T (S buffer handed back by the
+    // softmax warps as soon as S_g is in their registers).  Every stream runs two blocks ahead of its consumer,
+    // across item boundaries: inside a tensor-busy SM a tile lands ~2500 clk after its load is issued (440 clk on
+    // an otherwise idle SM with the tile in L2: tools/tma_latency.py), more than one block period.
+    for (int i = 0; i < K_STAGES && i < total_blocks; ++i) emit_k();
+    if (total_blocks > 0) issue_qk();
+    if (total_blocks > 1) issue_qk();
+    for (int g = 0; g < total_blocks; ++g) {
+      if (k_left > 0) emit_k();
+      if (q_left > 0) issue_qk();
+    }
+  } else if (warp == 1) {
+    // ===================== warp 1: V loads + PV issuer (whole warp walks the loop, one elected lane issues) =====
+    const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O += P V  (B = V, MN-major)
+    const uint32_t idesc_l = ig::umma_idesc_bf16(BQ, 8, 0, 0);    // L += P 1  (B = ones, K-major, N = 8)
     const uint32_t p_lo = ig::umma_desc_lo(smem_base + OFF_P);
     const uint32_t one_lo = ig::umma_desc_lo(smem_base + OFF_ONES);
     // V is consumed MN-major straight from its [kv, 64] tile: 16 kv rows of 128 bytes per K step, 8-row groups
     // 1024 B apart (LBO = SBO = 1024)
     const uint32_t v_lo = (((smem_base + OFF_V) & 0x3FFFF) >> 4) | ((1024u >> 4) << 16);
-    auto issue_qk = [&](int i) {
-      const int st = i % KV_STAGES, sb = i & 1;
-      ig::mbar_wait(&k_full[st], (i / KV_STAGES) & 1);
-      ig::mbar_wait(&s_free[sb], ((i >> 1) & 1) ^ 1);
-      ig::tc_fence_after();
-      const uint32_t dk = k_lo + st * (KV_BYTES >> 4);
-      const uint32_t d_s = tmem_base + COL_S + sb * BKV;
+    const int gstride = gridDim.x;
+    // V stream (its buffers are released by this warp's own PV commits)
+    int v_left = total_blocks, v_j = 0, v_w = blockIdx.x, v_st = 0, v_col = 0, v_row = 0;
+    uint32_t v_par = 1;
+    auto decode_v = [&]() {
+      const int bh = v_w / items_per_bh;
+      const int b = bh / heads, h = bh - b * heads;
+      v_col = 2 * D + h * HD, v_row = b * N;
+    };
+    if (total_blocks > 0) decode_v();
+    auto emit_v = [&]() {
+      ig::mbar_wait(&v_empty[v_st], v_par);
       if (ig::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < (ATTN_ABLATE == 7 ? 1 : HD / 16); ++k)
-          ig::umma_bf16(d_s, ig::umma_desc_pack(q_lo + 2 * k), ig::umma_desc_pack(dk + 2 * k), idesc, k > 0);
-        ig::umma_commit(&s_full[sb]);
-        ig::umma_commit(&k_empty[st]);
+        TRACE(0, 2, v_left);  // V load issued
+        ig::mbar_expect_tx(&v_full[v_st], KV_BYTES);
+        ig::tma_load_2d(smem + OFF_V + v_st * KV_BYTES, &tmkv, &v_full[v_st], v_col, v_row);
       }
       __syncwarp();
+      --v_left;
+      v_row += BKV;
+      if (++v_st == V_STAGES) v_st = 0, v_par ^= 1;
+      if (++v_j == nb) {
+        v_j = 0, v_w += gstride;
+        if (v_left > 0) decode_v();
+      }
     };
-    ig::mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (nb > 1) issue_qk(1);
-    for (int j = 0; j < nb; ++j) {
-      const int st = j % KV_STAGES, pb = j & 1;
-      // S_{j+2} = Q K_{j+2}^T goes first: it needs only the S buffer that the softmax warps hand back as soon as
-      // S_j is in their registers, not P_j -- so the scores of the next two blocks are always ready ahead of the
-      // softmax warps and the QK issue latency is off the P_j -> PV_j critical path.
-      PROF_T(m0);
-      if (j + 2 < nb) issue_qk(j + 2);
+    for (int i = 0; i < V_STAGES - 1 && i < total_blocks; ++i) emit_v();
+    int n = 0, j = 0, sv = 0, pb = 0;
+    uint32_t vf_par = 0, pf_par = 0;  // parities to wait for on v_full / p_full
+    for (int g = 0; g < total_blocks; ++g) {
       PROF_T(m1);
-      ig::mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-      ig::mbar_wait(&p_full[pb], (j >> 1) & 1);  // P_j is in smem and any rescale of O / L is finished
+      ig::mbar_wait(&v_full[sv], vf_par);
+      PROF_T(m1b);
+      TRACE(1, 14, g);  // V ready
+      PROF_ADD(12, m1, m1b);  // wait V_g
+      ig::mbar_wait(&p_full[pb], pf_par);  // P_g is in smem and any rescale of O / L is finished
+      // first block of an item overwrites O / L: the previous item's epilogue must have read them
+      if (j == 0 && n > 0) ig::mbar_wait(o_free, (n - 1) & 1);
       PROF_T(m2);
+      TRACE(1, 12, g);  // V and P ready
       ig::tc_fence_after();
       const uint32_t dp = p_lo + pb * (P_BYTES >> 4);
-      const uint32_t dv = v_lo + st * (KV_BYTES >> 4);
+      const uint32_t dv = v_lo + sv * (KV_BYTES >> 4);
       const uint32_t acc0 = j > 0 ? 1u : 0u;
       if (ig::elect_one()) {
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          // A = P_j: 128 rows x 64 kv (one swizzle atom column), 32 bytes per K step
+          // A = P_g: 128 rows x 64 kv (one swizzle atom column), 32 bytes per K step
           const uint64_t da = ig::umma_desc_pack(dp + 2 * k);
           if (ATTN_ABLATE != 6 || k == 0)
             ig::umma_bf16(tmem_base + COL_O, da, ig::umma_desc_pack(dv + k * (2048 >> 4)), idesc_o, k > 0 ? 1u : acc0);
@@ -205,14 +345,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
             ig::umma_bf16(tmem_base + COL_L, da, ig::umma_desc_pack(one_lo + 2 * k), idesc_l, k > 0 ? 1u : acc0);
         }
         ig::umma_commit(&o_done[pb]);
-        ig::umma_commit(&v_empty[st]);
+        ig::umma_commit(&v_empty[sv]);
         ig::umma_commit(&p_free[pb]);
       }
       __syncwarp();
       PROF_T(m3);
-      PROF_ADD(8, m0, m1);   // issue QK_{j+2} (incl. waits K, S free)
-      PROF_ADD(9, m1, m2);   // wait V_j, P_j
-      PROF_ADD(10, m2, m3);  // issue PV_j
+      TRACE(1, 13, g);  // PV issued
+      PROF_ADD(9, m1b, m2);  // wait P_g (, O free)
+      PROF_ADD(10, m2, m3);  // issue PV_g
+      if (++j == nb) j = 0, ++n;
+      if (++sv == V_STAGES) sv = 0, vf_par ^= 1;
+      pb ^= 1;
+      if (pb == 0) pf_par ^= 1;
+      // V_{g+2} goes into the buffer PV_{g-1} released (that commit was issued one iteration ago)
+      if (v_left > 0) emit_v();
     }
   } else {
     // ===================== softmax / output warps (one thread per query row) =====================
@@ -223,147 +369,152 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     const float jump = RESCALE_LOG2 / sl2;           // the same threshold in raw score units
     const uint32_t NEG_INF = 0xff800000u;
-    float m_ref = -INFINITY;
     uint32_t sc[64];
     uint32_t(&sa)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc);
     uint32_t(&sb2)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc + 32);
-
-    for (int j = 0; j < nb; ++j) {
-      const int kv0 = j * BKV, sb = j & 1;
-      const int nvalid = min(BKV, N - kv0);  // warp-uniform
-      PROF_T(c0);
-      ig::mbar_wait(&s_full[sb], (j >> 1) & 1);
-      PROF_T(c1);
-      ig::tc_fence_after();
-#if ATTN_ABLATE == 3
+    int g = 0;  // KV blocks consumed so far (all items): buffer index and barrier parity
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int qt = w % items_per_bh, bh = w / items_per_bh;
+      const int h = bh % heads, b = bh / heads;
+      const int row0 = b * N, q0 = qt * BQ;
+      float m_ref = -INFINITY;
+      for (int j = 0; j < nb; ++j, ++g) {
+        const int kv0 = j * BKV, sb = g & 1;
+        const uint32_t par = (g >> 1) & 1;
+        const int nvalid = min(BKV, N - kv0);  // warp-uniform
+        PROF_T(c0);
+        ig::mbar_wait(&s_full[sb], par);
+        PROF_T(c1);
+        TRACE(2, 20 + 100 * warp, g);  // S ready (every softmax warp)
+        ig::tc_fence_after();
+        ig::tmem_ld32(t_s + sb * BKV, sa);
+        ig::tmem_ld32(t_s + sb * BKV + 32, sb2);
+        ig::tmem_ld_wait();
+        // the scores are in registers: hand the S buffer back so QK^T of block g+2 can start
+        ig::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ig::mbar_arrive(&s_free[sb]);
+        PROF_T(c2);
+        if (nvalid < BKV) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
 #pragma unroll
-      for (int i = 0; i < 64; ++i) sc[i] = __float_as_uint(0.01f * (i + j + lane));
-#else
-      ig::tmem_ld32(t_s + sb * BKV, sa);
-      ig::tmem_ld32(t_s + sb * BKV + 32, sb2);
-      ig::tmem_ld_wait();
+          for (int i = 0; i < 64; ++i)
+            if (i >= nvalid) sc[i] = NEG_INF;
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sc[i + 4]), __uint_as_float(sc[i + 5])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sc[i + 6]), __uint_as_float(sc[i + 7])));
+        }
+        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (j == 0) {
+          m_ref = m_blk;  // PV_0 overwrites O / L (accumulate = 0): nothing to rescale
+        } else {
+          const bool need = m_blk > m_ref + jump;
+          if (__any_sync(0xffffffffu, need)) {
+            // ---- lazy rescale: O and L of this warp's 32 rows are multiplied by 2^(old - new) in TMEM.
+            // PV_{g-1} must have completed; PV_g cannot start before this warp arrives on p_full below.
+            const float m_new = need ? m_blk : m_ref;
+            const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 1 for rows that keep their reference
+            m_ref = m_new;
+            ig::mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            ig::tc_fence_after();
+            uint32_t t[32];
+#pragma unroll
+            for (int c = 0; c < HD; c += 32) {
+              ig::tmem_ld32(t_o + c, t);
+              ig::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+              ig::tmem_st32(t_o + c, t);
+            }
+            const uint32_t lv = ig::tmem_ld1(t_l);
+            ig::tmem_ld_wait();
+            ig::tmem_st1(t_l, __float_as_uint(__uint_as_float(lv) * alpha));
+            ig::tmem_st_wait();
+          }
+        }
+        const float mc = m_ref * sl2;
+        // ---- exponentials -> P_g (bf16, swizzled smem); fully masked 16-column groups are written as zeros
+        PROF_T(c3);
+        ig::mbar_wait(&p_free[sb], par ^ 1);
+        PROF_T(c4);
+        TRACE(2, 21 + 100 * warp, g);  // P buffer free, exps start
+        uint8_t* prow = smem + OFF_P + sb * P_BYTES + row * 128;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          uint32_t pk[8];
+          if (gq * 16 < nvalid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float p0 = exp2_or_ablate(fmaf(__uint_as_float(sc[gq * 16 + 2 * i]), sl2, -mc));
+              const float p1 = exp2_or_ablate(fmaf(__uint_as_float(sc[gq * 16 + 2 * i + 1]), sl2, -mc));
+              pk[i] = ig::pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = 0u;
+          }
+#if ATTN_ABLATE == 2
+          if (pk[0] == 0x12345678u)
 #endif
-      // the scores are in registers: hand the S buffer back so QK^T of block j+2 can start
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int chunk = gq * 2 + q;  // 16-byte chunk inside the 128-byte row
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        }
+        PROF_T(c5);
+#if ATTN_ABLATE != 10
+        ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
+#endif
+        ig::tc_fence_before();         // orders a rescale's tcgen05.st before the MMA warp's PV_g
+        __syncwarp();
+        if (lane == 0) ig::mbar_arrive(&p_full[sb]);
+        PROF_T(c6);
+        TRACE(2, 22 + 100 * warp, g);  // P_g published (every softmax warp)
+        PROF_ADD(0, c0, c1);  // wait S
+        PROF_ADD(1, c1, c2);  // TMEM load of S
+        PROF_ADD(2, c2, c3);  // mask + max (+ rescale)
+        PROF_ADD(3, c3, c4);  // wait P buffer free
+        PROF_ADD(4, c4, c5);  // exponentials + P stores
+        PROF_ADD(5, c5, c6);  // fences + arrive
+      }
+      // ---- item epilogue: O / L out of TMEM, then the accumulators are free for the next item's PV_0
+      PROF_T(e0);
+      ig::mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+      PROF_T(e1);
+      if (warp == 2) TRACE(2, 23, g);  // last PV done
+      ig::tc_fence_after();
+      ig::tmem_ld32(t_o, sa);
+      ig::tmem_ld32(t_o + 32, sb2);
+      const uint32_t lv = ig::tmem_ld1(t_l);
+      ig::tmem_ld_wait();
       ig::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ig::mbar_arrive(&s_free[sb]);
-      PROF_T(c2);
-      if (nvalid < BKV) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
+      if (lane == 0) ig::mbar_arrive(o_free);
+      const float inv = 1.f / __uint_as_float(lv);
+      const int qrow = q0 + row;
+      if (qrow < N) {
+        __nv_bfloat16* orow = out + (static_cast<int64_t>(row0) + qrow) * D + h * HD;
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= nvalid) sc[i] = NEG_INF;
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3])));
-        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sc[i + 4]), __uint_as_float(sc[i + 5])));
-        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sc[i + 6]), __uint_as_float(sc[i + 7])));
-      }
-#if ATTN_ABLATE == 4
-      const float m_blk = __uint_as_float(sc[lane & 63]);
-#else
-      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-#endif
-      if (j == 0) {
-        m_ref = m_blk;
-      } else {
-        const bool need = m_blk > m_ref + jump;
-        if (__any_sync(0xffffffffu, need)) {
-          // ---- lazy rescale: O and L of this warp's 32 rows are multiplied by 2^(old - new) in TMEM.
-          // PV_{j-1} must have completed; PV_j cannot start before this warp arrives on p_full below.
-          const float m_new = need ? m_blk : m_ref;
-          const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 1 for rows that keep their reference
-          m_ref = m_new;
-          ig::mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          ig::tc_fence_after();
-          uint32_t t[32];
-#pragma unroll
-          for (int c = 0; c < HD; c += 32) {
-            ig::tmem_ld32(t_o + c, t);
-            ig::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            ig::tmem_st32(t_o + c, t);
-          }
-          const uint32_t lv = ig::tmem_ld1(t_l);
-          ig::tmem_ld_wait();
-          ig::tmem_st1(t_l, __float_as_uint(__uint_as_float(lv) * alpha));
-          ig::tmem_st_wait();
+        for (int q = 0; q < 8; ++q) {
+          uint4 o;
+          o.x = ig::pack_bf16(__uint_as_float(sc[8 * q + 0]) * inv, __uint_as_float(sc[8 * q + 1]) * inv);
+          o.y = ig::pack_bf16(__uint_as_float(sc[8 * q + 2]) * inv, __uint_as_float(sc[8 * q + 3]) * inv);
+          o.z = ig::pack_bf16(__uint_as_float(sc[8 * q + 4]) * inv, __uint_as_float(sc[8 * q + 5]) * inv);
+          o.w = ig::pack_bf16(__uint_as_float(sc[8 * q + 6]) * inv, __uint_as_float(sc[8 * q + 7]) * inv);
+          reinterpret_cast<uint4*>(orow)[q] = o;
         }
       }
-      const float mc = m_ref * sl2;
-      // ---- exponentials -> P_j (bf16, swizzled smem); fully masked 16-column groups are written as zeros
-      PROF_T(c3);
-      ig::mbar_wait(&p_free[sb], ((j >> 1) & 1) ^ 1);
-      PROF_T(c4);
-      uint8_t* prow = smem + OFF_P + sb * P_BYTES + row * 128;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t pk[8];
-        if (g * 16 < nvalid) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float p0 = exp2_or_ablate(fmaf(__uint_as_float(sc[g * 16 + 2 * i]), sl2, -mc));
-            const float p1 = exp2_or_ablate(fmaf(__uint_as_float(sc[g * 16 + 2 * i + 1]), sl2, -mc));
-            pk[i] = ig::pack_bf16(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = 0u;
-        }
-#if ATTN_ABLATE == 2
-        if (pk[0] == 0x12345678u)
-#endif
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int chunk = g * 2 + q;  // 16-byte chunk inside the 128-byte row
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      PROF_T(c5);
-      ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
-      ig::tc_fence_before();         // orders a rescale's tcgen05.st before the MMA warp's PV_j
-      __syncwarp();
-      if (lane == 0) ig::mbar_arrive(&p_full[sb]);
-      PROF_T(c6);
-      if (j == 0) { PROF_ADD(6, c0, c1); PROF_ADD(12, cta0, c0); }  // first block: wait S_0; kernel start -> softmax loop
-      PROF_ADD(0, c0, c1);  // wait S_j
-      PROF_ADD(1, c1, c2);  // TMEM load of S_j
-      PROF_ADD(2, c2, c3);  // mask + max (+ rescale)
-      PROF_ADD(3, c3, c4);  // wait P buffer free
-      PROF_ADD(4, c4, c5);  // exponentials + P stores
-      PROF_ADD(5, c5, c6);  // fences + arrive
+      PROF_T(e2);
+      if (warp == 2) TRACE(2, 24, g);  // item stored
+      PROF_ADD(7, e0, e1);   // wait for the item's last PV
+      PROF_ADD(13, e1, e2);  // O load, normalise, store
     }
-    // ---- epilogue: O / L
-    PROF_T(e0);
-    ig::mbar_wait(&o_done[(nb - 1) & 1], ((nb - 1) >> 1) & 1);
-    PROF_T(e1);
-    PROF_ADD(7, e0, e1);  // wait for the last PV
-    ig::tc_fence_after();
-    ig::tmem_ld32(t_o, sa);
-    ig::tmem_ld32(t_o + 32, sb2);
-    const uint32_t lv = ig::tmem_ld1(t_l);
-    ig::tmem_ld_wait();
-    const float inv = 1.f / __uint_as_float(lv);
-    const int qrow = q0 + row;
-    if (qrow < N) {
-      __nv_bfloat16* orow = out + (static_cast<int64_t>(row0) + qrow) * D + h * HD;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 o;
-        o.x = ig::pack_bf16(__uint_as_float(sc[8 * q + 0]) * inv, __uint_as_float(sc[8 * q + 1]) * inv);
-        o.y = ig::pack_bf16(__uint_as_float(sc[8 * q + 2]) * inv, __uint_as_float(sc[8 * q + 3]) * inv);
-        o.z = ig::pack_bf16(__uint_as_float(sc[8 * q + 4]) * inv, __uint_as_float(sc[8 * q + 5]) * inv);
-        o.w = ig::pack_bf16(__uint_as_float(sc[8 * q + 6]) * inv, __uint_as_float(sc[8 * q + 7]) * inv);
-        reinterpret_cast<uint4*>(orow)[q] = o;
-      }
-    }
-#ifdef ATTN_PROFILE
-    { PROF_T(e2); PROF_ADD(13, e1, e2); }  // O load, normalise, store
-#endif
   }
 
   ig::tc_fence_before();
@@ -386,10 +537,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
 }  // namespace attn
 
 #ifdef ATTN_PROFILE
+extern "C" int ig_attention_trace(long long* out, int* counts) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, attn::g_attn_trace, sizeof(long long) * 3 * 4096 * 3);
+  cudaMemcpyFromSymbol(counts, attn::g_attn_trace_n, sizeof(int) * 3);
+  int z[3] = {0, 0, 0};
+  cudaMemcpyToSymbol(attn::g_attn_trace_n, z, sizeof(z));
+  return 0;
+}
 extern "C" int ig_attention_profile(unsigned long long* out16) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out16, attn::g_attn_prof, sizeof(unsigned long long) * 16);
-  unsigned long long z[16] = {0};
+  cudaMemcpyFromSymbol(out16, attn::g_attn_prof, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
   cudaMemcpyToSymbol(attn::g_attn_prof, z, sizeof(z));
   return 0;
 }
@@ -398,7 +557,6 @@ extern "C" int ig_attention_profile(unsigned long long* out16) {
 namespace ops {
 int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t st) {
   IG_REQUIRE(B >= 1 && N >= 1 && heads >= 1, IG_ESHAPE, "attention: bad shape B=%d N=%d heads=%d", B, N, heads);
-  IG_REQUIRE(B <= 65535 && heads <= 65535, IG_ESHAPE, "attention: grid too large");
   const int D = heads * attn::HD;
   static bool configured = false;
   if (!configured) {
@@ -409,9 +567,13 @@ int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t 
   CUtensorMap tmq, tmkv;
   IG_TRY(ig_make_tmap_bf16(&tmq, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BQ, 64));
   IG_TRY(ig_make_tmap_bf16(&tmkv, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BKV, 64));
-  dim3 grid((N + attn::BQ - 1) / attn::BQ, heads, B);
+  const int nqt = (N + attn::BQ - 1) / attn::BQ;
+  IG_REQUIRE(static_cast<int64_t>(nqt) * heads * B < (1ll << 31), IG_ESHAPE, "attention: too many work items");
+  const int total_items = nqt * heads * B;
+  const int grid = total_items < 2 * ig_num_sms() ? total_items : 2 * ig_num_sms();
   ig::ProfScope prof(ig::PROF_ATTENTION, st);
-  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_TOTAL, st>>>(tmq, tmkv, static_cast<__nv_bfloat16*>(out), N, D);
+  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_TOTAL, st>>>(tmq, tmkv, static_cast<__nv_bfloat16*>(out), N, D,
+                                                                      nqt, heads, total_items);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }
@@ -422,3 +584,35 @@ extern "C" int ig_attention(const void* qkv, void* out, int B, int N, int heads,
   IG_REQUIRE(qkv && out, IG_EINVAL, "ig_attention: null pointer");
   return ops::attention(qkv, out, B, N, heads, static_cast<cudaStream_t>(stream));
 }
+
+#ifdef ATTN_PROFILE
+// TMA latency probe: one thread loads [64 x 64] bf16 tiles of the qkv matrix (the K / V box of the attention kernel)
+// one at a time and records issue -> mbarrier completion in clock cycles.  reps 0..n-1 touch new tiles (cold: DRAM or
+// whatever L2 holds), reps n..2n-1 touch the same tiles again (L2 hits).
+namespace attn {
+__global__ void tma_latency_kernel(const __grid_constant__ CUtensorMap tmkv, long long* out, int n, int row_step, int col0) {
+  __shared__ __align__(1024) uint8_t tile[KV_BYTES];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    ig::tma_prefetch_desc(&tmkv);
+    ig::mbar_init(&bar, 1);
+    ig::fence_barrier_init();
+    for (int i = 0; i < 2 * n; ++i) {
+      const int r = (i % n) * row_step + blockIdx.x * 64;
+      const long long t0 = clock64();
+      ig::mbar_expect_tx(&bar, KV_BYTES);
+      ig::tma_load_2d(tile, &tmkv, &bar, col0, r);
+      ig::mbar_wait(&bar, i & 1);
+      out[blockIdx.x * 2 * n + i] = clock64() - t0;
+    }
+  }
+}
+}  // namespace attn
+extern "C" int ig_debug_tma_latency(const void* qkv, int rows, int D3, long long* out_dev, int n, int row_step, int col0, int ctas) {
+  CUtensorMap tmkv;
+  IG_TRY(ig_make_tmap_bf16(&tmkv, qkv, rows, D3, D3, attn::BKV, 64));
+  attn::tma_latency_kernel<<<ctas, 32>>>(tmkv, out_dev, n, row_step, col0);
+  IG_CUDA_OK(cudaDeviceSynchronize());
+  return IG_OK;
+}
+#endif

@@ -97,14 +97,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes or ~`ns` elapse,
+// instead of returning after its short default limit.  A waiting role warp (TMA producer, MMA issuer) that polls
+// without the hint issues a try_wait + branch every few cycles and takes issue slots from the compute warps of
+// its scheduler: in the attention kernel a third of all executed instructions were such polls, and the two
+// softmax warps that share a scheduler with the producer / MMA warps fell thousands of cycles behind the others.
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging
 // the GPU.  ~4 s budget, far above any kernel in this library.  The spin loop lives out of line
 // so the hot path (barrier already complete) is a single try_wait.
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   unsigned long long t0 = 0;
   uint32_t spins = 0;
+#ifndef IG_WAIT_MODE
+#define IG_WAIT_MODE 0
+#endif
+#if IG_WAIT_MODE == 0
+  while (!mbar_try_wait_parked(bar, parity, 20000u)) {
+#elif IG_WAIT_MODE == 1
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3fff) == 0) {
+#else
+  while (!mbar_try_wait_parked(bar, parity, 200u)) {
+#endif
+    if ((++spins & 0x3f) == 0) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
@@ -158,6 +183,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a 2-D box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                             int32_t c0, int32_t c1, int32_t c2, int32_t c3) {

@@ -9,7 +9,7 @@ lib = _lib.load()
 dev = torch.device("cuda:0")
 B, N, H = 64, 589, 12
 qkv = torch.randn(B * N, 3 * H * 64, device=dev).bfloat16()
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 32)()
 for _ in range(3):
     ops.attention(qkv, B, N, H)
 lib.ig_attention_profile(buf)
@@ -19,10 +19,13 @@ v = list(buf)
 ctas = v[15]
 nb = (N + 63) // 64
 names = ["softmax: wait S_j", "softmax: TMEM load S_j", "softmax: mask+max(+rescale)", "softmax: wait P free", "softmax: exps + P stores",
-         "softmax: fences + arrive", "", "", "mma: issue QK_j+2 (incl. waits K, S free)", "mma: wait V_j, P_j", "mma: issue PV_j"]
+         "softmax: fences + arrive", "", "", "warp0: issue QK_g+2", "warp1: wait P_g", "warp1: issue PV_g"]
 print(f"CTAs {ctas}, KV blocks per CTA {nb}, mean CTA lifetime {v[14]/ctas:.0f} clk")
-print(f"  per CTA: kernel start -> softmax loop {v[12]/ctas:.0f} clk, wait S_0 {v[6]/ctas:.0f}, wait last PV {v[7]/ctas:.0f}, "
-      f"O epilogue {v[13]/ctas:.0f}, softmax loop total {sum(v[0:6])/ctas:.0f}")
+items = -(-(64 * 12 * 5) // ctas)
+print(f"  per item (~{items} per CTA): wait last PV {v[7]/ctas/items:.0f}, O epilogue {v[13]/ctas/items:.0f}; per block: "
+      f"QK wait Q/K {v[11]/ctas/items/nb:.0f}, QK wait S free {v[6]/ctas/items/nb:.0f}, PV wait V {v[12]/ctas/items/nb:.0f}")
+print(f"  warp0 per block: wait V buffer free {v[16]/ctas/items/nb:.0f}, issue V load {v[17]/ctas/items/nb:.0f}, V load issue->landed (mode 4 only) {v[18]/ctas/items/nb:.0f}")
+nb *= items
 for i, n in enumerate(names):
     if n:
         print(f"  {n:45s} {v[i]/ctas/nb:8.1f} clk per KV block")
