@@ -159,8 +159,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   // Both issuing warps need these (uniform values; descriptors are formed ADDITIVELY from base words computed
   // once: start address >> 4 in the low word, a stage / buffer / K-step is a constant added to it, so a UMMA costs
   // one or two uniform-datapath adds instead of a shift-mask-or chain per operand).
-  const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                       static_cast<int>(gridDim.x);
+  // A CTA owns a CONTIGUOUS run of work items (query tile fastest, then head, then batch element): consecutive
+  // items share their K / V tiles (the five query tiles of one (batch, head)) or at least the batch element's
+  // pages.  Measured neutral against dealing items round-robin (171 vs 170 us at B = 64): what still delays PV is a
+  // heavy tail of the K / V tile loads -- ~8 % of them land > 10 000 clk after their issue (in-kernel probe,
+  // tools/attn_profile.py), against 440 clk (L2 hit) / 1100 clk (DRAM) for the same box on an idle SM
+  // (tools/tma_latency.py) -- spread over all block indices of an item; open question for the next round.
+  const int items_base = total_items / static_cast<int>(gridDim.x), items_rem = total_items % static_cast<int>(gridDim.x);
+  const int my_items = items_base + (static_cast<int>(blockIdx.x) < items_rem ? 1 : 0);
+  const int w_begin = static_cast<int>(blockIdx.x) * items_base + min(static_cast<int>(blockIdx.x), items_rem);
   const int total_blocks = my_items * nb;
   const uint32_t smem_base = ig::smem_u32(smem);
 
@@ -181,9 +188,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     // ring / parity / coordinate state is CARRIED and updated incrementally, an item is decoded (three integer
     // divisions) once per item and not per block.  With divisions and modulos per block this warp needed ~3000 clk
     // per KV block and was the slowest actor of the CTA (event trace, tools/attn_trace.py).
-    const int gstride = gridDim.x;
     // K stream
-    int k_left = total_blocks, k_j = 0, k_w = blockIdx.x, k_st = 0, k_col = 0, k_row = 0;
+    int k_left = total_blocks, k_j = 0, k_w = w_begin, k_st = 0, k_col = 0, k_row = 0;
     uint32_t k_par = 1;  // parity to wait for on k_empty (fresh barrier: passes)
     auto decode = [&](int w, int& col_h, int& row0, int& qrow) {
       const int bh = w / items_per_bh, qt = w - bh * items_per_bh;
@@ -213,7 +219,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       k_row += BKV;
       if (++k_st == K_STAGES) k_st = 0, k_par ^= 1;
       if (++k_j == nb) {
-        k_j = 0, k_w += gstride;
+        k_j = 0, ++k_w;
         if (k_left > 0) {
           int ch, r0;
           decode(k_w, ch, r0, dummy_q);
@@ -259,7 +265,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
         // the next item -- two blocks before that item's first QK^T is issued.
         if (q_left > 0) {
           int ch, r0, qrow;
-          decode(static_cast<int>(blockIdx.x) + (q_n + 1) * gstride, ch, r0, qrow);
+          decode(w_begin + q_n + 1, ch, r0, qrow);
           ig::mbar_wait(q_empty, q_n & 1);
           if (ig::elect_one()) {
             ig::mbar_expect_tx(q_full, Q_BYTES);
@@ -290,9 +296,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     // V is consumed MN-major straight from its [kv, 64] tile: 16 kv rows of 128 bytes per K step, 8-row groups
     // 1024 B apart (LBO = SBO = 1024)
     const uint32_t v_lo = (((smem_base + OFF_V) & 0x3FFFF) >> 4) | ((1024u >> 4) << 16);
-    const int gstride = gridDim.x;
     // V stream (its buffers are released by this warp's own PV commits)
-    int v_left = total_blocks, v_j = 0, v_w = blockIdx.x, v_st = 0, v_col = 0, v_row = 0;
+    int v_left = total_blocks, v_j = 0, v_w = w_begin, v_st = 0, v_col = 0, v_row = 0;
     uint32_t v_par = 1;
     auto decode_v = [&]() {
       const int bh = v_w / items_per_bh;
@@ -300,8 +305,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       v_col = 2 * D + h * HD, v_row = b * N;
     };
     if (total_blocks > 0) decode_v();
+#ifdef ATTN_PROFILE
+    long long v_issue_t[V_STAGES] = {0, 0, 0};
+#endif
     auto emit_v = [&]() {
       ig::mbar_wait(&v_empty[v_st], v_par);
+#ifdef ATTN_PROFILE
+      v_issue_t[v_st] = clock64();
+#endif
       if (ig::elect_one()) {
         TRACE(0, 2, v_left);  // V load issued
         ig::mbar_expect_tx(&v_full[v_st], KV_BYTES);
@@ -312,7 +323,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       v_row += BKV;
       if (++v_st == V_STAGES) v_st = 0, v_par ^= 1;
       if (++v_j == nb) {
-        v_j = 0, v_w += gstride;
+        v_j = 0, ++v_w;
         if (v_left > 0) decode_v();
       }
     };
@@ -321,8 +332,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     uint32_t vf_par = 0, pf_par = 0;  // parities to wait for on v_full / p_full
     for (int g = 0; g < total_blocks; ++g) {
       PROF_T(m1);
+#ifdef ATTN_PROFILE
+      const bool v_was_ready = ig::mbar_try_wait(&v_full[sv], vf_par);
+#endif
       ig::mbar_wait(&v_full[sv], vf_par);
       PROF_T(m1b);
+#ifdef ATTN_PROFILE
+      if (!v_was_ready) { PROF_ADD(19, v_issue_t[sv], m1b); PROF_ADD(20, 0, 1); PROF_ADD(22 + (j < 9 ? j : 9), 0, 1); }
+      PROF_ADD(21, 0, 1);
+#endif
       TRACE(1, 14, g);  // V ready
       PROF_ADD(12, m1, m1b);  // wait V_g
       ig::mbar_wait(&p_full[pb], pf_par);  // P_g is in smem and any rescale of O / L is finished
@@ -373,7 +391,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     uint32_t(&sa)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc);
     uint32_t(&sb2)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc + 32);
     int g = 0;  // KV blocks consumed so far (all items): buffer index and barrier parity
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    for (int w = w_begin; w < w_begin + my_items; ++w) {
       const int qt = w % items_per_bh, bh = w / items_per_bh;
       const int h = bh % heads, b = bh / heads;
       const int row0 = b * N, q0 = qt * BQ;

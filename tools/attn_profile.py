@@ -25,6 +25,8 @@ items = -(-(64 * 12 * 5) // ctas)
 print(f"  per item (~{items} per CTA): wait last PV {v[7]/ctas/items:.0f}, O epilogue {v[13]/ctas/items:.0f}; per block: "
       f"QK wait Q/K {v[11]/ctas/items/nb:.0f}, QK wait S free {v[6]/ctas/items/nb:.0f}, PV wait V {v[12]/ctas/items/nb:.0f}")
 print(f"  warp0 per block: wait V buffer free {v[16]/ctas/items/nb:.0f}, issue V load {v[17]/ctas/items/nb:.0f}, V load issue->landed (mode 4 only) {v[18]/ctas/items/nb:.0f}")
+print(f"  V loads: {v[20]} of {v[21]} not landed when PV_g wanted them; for those, issue -> landed = {v[19]/max(1,v[20]):.0f} clk")
+print("  late V loads by block index within the item:", [int(x) for x in v[22:32]])
 nb *= items
 for i, n in enumerate(names):
     if n:
