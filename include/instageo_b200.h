@@ -137,7 +137,8 @@ int ig_model_finalize(ig_model* m, void* stream);
 size_t ig_model_workspace_bytes(const ig_model* m, int batch);
 /* x: [B, C, T, 224, 224] float32 (x_dtype IG_F32), or tubelet rows written by
  * ig_preprocess(out_patch) (x_dtype IG_BF16).  logits [B, nc, 224, 224] float32 or NULL;
- * argmax [B, 224, 224] int8 or NULL; feats [B, D*T, 14, 14] float32 or NULL. */
+ * argmax [B, 224, 224] int8 or NULL = torch.argmax(logits, dim=1) fused into the head epilogue
+ * (instageo/model/infer_utils.py:96-101); feats [B, D*T, 14, 14] float32 or NULL. */
 int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits,
                      int8_t* argmax, float* feats, void* workspace, size_t workspace_bytes,
                      void* stream);

@@ -61,3 +61,29 @@ def test_state_dict_is_drop_in():
     assert "prithvi_encoder.temporal_embed_enc.scale" in tl.state_dict()
     with pytest.raises(NotImplementedError):
         PrithviSeg(load_pretrained_weights=False, variant="prithvi_eo_v2_600")
+
+
+def test_new_host_mirrors_refuse_cpu():
+    """§8(f) mirrors (metrics, chip masking): same no-fallback rule -- without CUDA they raise, they never compute on the host."""
+    import numpy as np
+    from instageo_b200.data import apply_mask, create_chip, mask_segmentation_map
+    from instageo_b200.model.metrics import RunningAUC, RunningConfusionMatrix, RunningRegressionMetrics
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    for cls, args in ((RunningConfusionMatrix, (3,)), (RunningAUC, (3,)), (RunningRegressionMetrics, ())):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            cls(*args)
+    chip = np.zeros((6, 8, 8), dtype=np.int16)
+    for fn in (lambda: create_chip(chip, np.zeros((1, 8, 8), np.uint8)), lambda: apply_mask(chip, np.zeros((1, 8, 8), np.uint8), 0),
+               lambda: mask_segmentation_map(chip, np.zeros((8, 8), np.int8), 0)):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            fn()
+
+
+def test_header_cites_reference_for_every_entry_point():
+    """every compute entry point of the C ABI names the reference interface it replaces (file:line)."""
+    src = open(os.path.join(ROOT, "include", "instageo_b200.h")).read()
+    for ref in ("instageo/model/dataloader.py:495-524", "instageo/model/model.py:292-419", "instageo/model/infer_utils.py:96-101",
+                "instageo/model/metrics.py:86-108", "instageo/model/metrics.py:209-244", "instageo/model/segmentation.py:117-156",
+                "instageo/model/segmentation.py:202-213", "instageo/data/data_pipeline.py:229-267", "instageo/data/hls_utils.py:359-403"):
+        assert ref in src, ref
