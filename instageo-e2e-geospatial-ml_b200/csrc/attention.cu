@@ -159,15 +159,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   // Both issuing warps need these (uniform values; descriptors are formed ADDITIVELY from base words computed
   // once: start address >> 4 in the low word, a stage / buffer / K-step is a constant added to it, so a UMMA costs
   // one or two uniform-datapath adds instead of a shift-mask-or chain per operand).
-  // A CTA owns a CONTIGUOUS run of work items (query tile fastest, then head, then batch element): consecutive
-  // items share their K / V tiles (the five query tiles of one (batch, head)) or at least the batch element's
-  // pages.  Measured neutral against dealing items round-robin (171 vs 170 us at B = 64): what still delays PV is a
-  // heavy tail of the K / V tile loads -- ~8 % of them land > 10 000 clk after their issue (in-kernel probe,
-  // tools/attn_profile.py), against 440 clk (L2 hit) / 1100 clk (DRAM) for the same box on an idle SM
-  // (tools/tma_latency.py) -- spread over all block indices of an item; open question for the next round.
-  const int items_base = total_items / static_cast<int>(gridDim.x), items_rem = total_items % static_cast<int>(gridDim.x);
-  const int my_items = items_base + (static_cast<int>(blockIdx.x) < items_rem ? 1 : 0);
-  const int w_begin = static_cast<int>(blockIdx.x) * items_base + min(static_cast<int>(blockIdx.x), items_rem);
+  // Work items are dealt ROUND-ROBIN (item n of this CTA is w_begin + n * w_step): the five query tiles of one
+  // (batch, head) then run on five CTAs at the same time and share their K / V tiles through L2 -- DRAM reads equal
+  // the qkv matrix once (174 MB at B = 64).  Contiguous runs per CTA were measured too: same time, but the K / V
+  // tiles of a (batch, head) were evicted between its query tiles and DRAM reads rose to 308 MB (ncu).
+  // What still delays PV is a heavy tail of the K / V tile loads -- ~8 % of them land > 10 000 clk after their issue
+  // (in-kernel probe, tools/attn_profile.py), against 440 clk (L2 hit) / 1100 clk (DRAM) for the same box on an
+  // idle SM (tools/tma_latency.py), spread over all block indices of an item; open question for the next round.
+  const int w_begin = blockIdx.x, w_step = gridDim.x;
+  const int my_items = (total_items - w_begin + w_step - 1) / w_step;
   const int total_blocks = my_items * nb;
   const uint32_t smem_base = ig::smem_u32(smem);
 
@@ -219,7 +219,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       k_row += BKV;
       if (++k_st == K_STAGES) k_st = 0, k_par ^= 1;
       if (++k_j == nb) {
-        k_j = 0, ++k_w;
+        k_j = 0, k_w += w_step;
         if (k_left > 0) {
           int ch, r0;
           decode(k_w, ch, r0, dummy_q);
@@ -265,7 +265,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
         // the next item -- two blocks before that item's first QK^T is issued.
         if (q_left > 0) {
           int ch, r0, qrow;
-          decode(w_begin + q_n + 1, ch, r0, qrow);
+          decode(w_begin + (q_n + 1) * w_step, ch, r0, qrow);
           ig::mbar_wait(q_empty, q_n & 1);
           if (ig::elect_one()) {
             ig::mbar_expect_tx(q_full, Q_BYTES);
@@ -323,7 +323,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       v_row += BKV;
       if (++v_st == V_STAGES) v_st = 0, v_par ^= 1;
       if (++v_j == nb) {
-        v_j = 0, ++v_w;
+        v_j = 0, v_w += w_step;
         if (v_left > 0) decode_v();
       }
     };
@@ -391,7 +391,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     uint32_t(&sa)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc);
     uint32_t(&sb2)[32] = *reinterpret_cast<uint32_t(*)[32]>(sc + 32);
     int g = 0;  // KV blocks consumed so far (all items): buffer index and barrier parity
-    for (int w = w_begin; w < w_begin + my_items; ++w) {
+    for (int w = w_begin; w < total_items; w += w_step) {
       const int qt = w % items_per_bh, bh = w / items_per_bh;
       const int h = bh % heads, b = bh / heads;
       const int row0 = b * N, q0 = qt * BQ;

@@ -36,6 +36,18 @@ def main(what, iters=4):
     elif what == "attn":
         qkv = torch.randn(64 * 589, 3 * 768, device=dev).bfloat16()
         fn = lambda: ops.attention(qkv, 64, 589, 12)  # noqa: E731
+    elif what.startswith("segm"):   # fused eval step: confusion (+ ROC histograms for "segm_auc")
+        from instageo_b200.model.metrics import RunningAUC, RunningConfusionMatrix, segmentation_eval_update
+        lg = torch.randn(64, 13, 224, 224, device=dev) * 3
+        lab = torch.randint(0, 13, (64, 224, 224), device=dev)
+        cm, auc = RunningConfusionMatrix(13, -100, device=dev), RunningAUC(13, device=dev)
+        fn = lambda: segmentation_eval_update(lg, lab, cm, auc if what == "segm_auc" else None)  # noqa: E731
+    elif what == "chipmask":
+        from instageo_b200.data import create_chip
+        tile = torch.randint(-100, 10200, (18, 3660, 3660), device=dev, dtype=torch.int16)
+        fm = (torch.rand((3, 3660, 3660), device=dev) < 0.2).to(torch.uint8) * 2
+        seg = torch.randint(-1, 5, (3660, 3660), device=dev, dtype=torch.int8)
+        fn = lambda: create_chip(tile, fm, seg, "each")  # noqa: E731
     elif what == "ln":
         x = torch.randn(64 * 589, 768, device=dev)
         g, b = torch.randn(768, device=dev), torch.randn(768, device=dev)
