@@ -161,3 +161,22 @@ def test_predict_step_probability_and_regression_head(cuda_dev, T, nc):
         assert (yr.cpu() - refr).abs().max().item() < TOL
         with pytest.raises(RuntimeError, match="classification head"):
             r.predict_proba(x.to(cuda_dev))
+
+
+@pytest.mark.parametrize("variant,T,nc,B", [("prithvi_eo_v1_100", 1, 2, 2), ("prithvi_eo_v1_100", 3, 13, 1),
+                                            ("prithvi_eo_v2_300", 3, 13, 1)])
+def test_full_depth_configs_vs_oracle(cuda_dev, variant, T, nc, B):
+    """BASELINE.json configs[0..2] at FULL depth (12 / 12 / 24 blocks, default and stress init): the bf16 engine against
+    the fp32 CPU oracle within the north-star budget (2e-2 max-abs on logits), argmax identical outside ties."""
+    for stress in (False, True):
+        m, sd = _build(variant, T, nc, -1, cuda_dev, seed=3, stress=stress)
+        x = torch.randn(B, 6, T, 224, 224, generator=torch.Generator().manual_seed(7 + T))
+        ref = P.prithvi_seg_forward(x, sd, P.VARIANTS[variant][2], T)
+        y = m(x.to(cuda_dev)).cpu()
+        eps = (y - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert eps < TOL, f"{variant} T={T} stress={stress}: logits max-abs {eps} (|logits| up to {scale})"
+        excluded = _argmax_check(m.predict(x.to(cuda_dev)), ref, eps)
+        print(f"{variant} T={T} nc={nc} stress={stress}: max-abs {eps:.3e} of {scale:.2f}, tie-excluded pixels {excluded:.4f}")
+        del m
+        torch.cuda.empty_cache()
