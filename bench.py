@@ -173,7 +173,7 @@ def run_tile(args):
     d_tile = tile.to(dev)
     # the nodata comparison happens AFTER the constant multiplier (dataloader.py:741, 899 -- SURVEY F10), so the
     # tile is normalised in raw DN units (statistics x 1e4, multiplier 1.0) to keep -9999 recognisable
-    kw = dict(window_size=(224, 224), stride=args.stride, batch_size=64, mean=[m * 1e4 for m in mean],
+    kw = dict(window_size=(224, 224), stride=args.stride, batch_size=args.tile_batch, mean=[m * 1e4 for m in mean],
               std=[s * 1e4 for s in std], constant_multiplier=1.0, no_data_value=-9999)
     n_win_total = len(ops.window_origins(H, 224, args.stride, True)) ** 2
 
@@ -210,11 +210,13 @@ def run_tile(args):
     _lib.profile_enable(False)
     # end to end: host tile in (pinned), host class map out
     pinned = tile.pin_memory()
+    res = torch.empty((H, W), dtype=torch.int8).pin_memory()   # pinned result buffer: D2H at PCIe speed, no staging copy
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = IU.sliding_window_inference_sharded(pinned.to(dev, non_blocking=True), model, rank, world, **kw).cpu()
-    torch.cuda.synchronize()
+        res.copy_(IU.sliding_window_inference_sharded(pinned.to(dev, non_blocking=True), model, rank, world, **kw),
+                  non_blocking=True)
+        torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -394,6 +396,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="chips_v1_100m_t3", choices=sorted(WORKLOADS) + ["tile_3660", "chipset_100k"])
     ap.add_argument("--stride", type=int, default=224, help="tile_3660: sliding-window stride")
+    ap.add_argument("--tile-batch", type=int, default=256, help="tile_3660: windows per model call (at most)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 1 if args.workload == "chipset_100k" else 20

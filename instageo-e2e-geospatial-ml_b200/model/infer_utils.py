@@ -163,8 +163,12 @@ def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224)
     win_t = torch.tensor(wins, dtype=torch.int32, device=device).reshape(-1, 3)
     logits = torch.empty((n_win, nc, win, win), dtype=torch.float32, device=device)
     fm = None if fmask is None else _to_device(fmask, device).unsqueeze(0)
-    for s in range(0, n_win, batch_size):
-        e = min(n_win, s + batch_size)
+    # equal-sized model calls of at most batch_size windows (289 windows, batch 256 -> 145 + 144, not 256 + 33:
+    # a small tail call runs the persistent GEMMs at a fraction of a wave)
+    n_calls = max(1, -(-n_win // batch_size))
+    per_call = -(-n_win // n_calls)
+    for s in range(0, n_win, per_call):
+        e = min(n_win, s + per_call)
         pre = ops.preprocess(tile.unsqueeze(0), spec, windows=win_t[s:e], win=win, want_f32=False,
                              want_patches=True, fmask=fm, fmask_bits=fmask_bits,
                              masking_strategy=masking_strategy)
