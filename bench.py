@@ -143,8 +143,8 @@ def run_reference(args):
 
 def run_tile(args):
     """BASELINE.json configs[3]: sliding-window inference over a synthetic 3660 x 3660 x 6 int16 HLS tile with a
-    nodata wedge, Prithvi-V1-100M T=1 flood head (2 classes), row-stripe sharded over the ranks (halo recompute),
-    one int8 all-gather.  One step = the whole tile; value = windows (224-px chips) per second over all ranks."""
+    nodata wedge, Prithvi-V1-100M T=1 flood head (2 classes); ranks split the window rows and the output row stripes,
+    exchange the window rows that straddle a stripe boundary (NCCL send/recv) and all-gather the int8 stripes.  One step = the whole tile; value = windows (224-px chips) per second over all ranks."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -229,7 +229,9 @@ def run_tile(args):
              "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
              "config": {"workload": f"tile_3660x3660x6_int16_stride{args.stride}: sliding windows -> normalise/mask -> "
                                     "PrithviSeg V1-100M T=1 nc=2 -> overlap-average stitch -> int8 map",
-                        "windows": n_win_total, "parallelism": f"row stripes x{world} (halo recompute), int8 all-gather",
+                        "windows": n_win_total, "windows_per_call": args.tile_batch,
+                        "parallelism": (f"window rows and output row stripes x{world}: boundary window rows exchanged by NCCL send/recv "
+                                        "(no recompute), int8 stripe all-gather; bit-identical to 1 GPU") if world > 1 else "single GPU",
                         "l2": "tile 80 MB + window logits 116-411 MB + >1 GB activations per step, larger than L2"},
              "clocks": clocks,
              "e2e": {"value": n_win_total * args.steps / dt.item(), "unit": "chips/s", "h2d_bytes_per_step": 6 * H * W * 2,

@@ -128,13 +128,16 @@ def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224)
                              constant_multiplier: float = 1.0, no_data_value: Optional[float] = None,
                              nodata_class: int = -1, rows: Optional[tuple[int, int]] = None,
                              return_tensor: bool = False, fmask=None, fmask_bits: int = 0,
-                             masking_strategy: str = "each"):
+                             masking_strategy: str = "each", exchange: Optional[tuple[int, int]] = None):
     """Overlap-averaged class map of a raw tile [T*C (or more bands), H, W] (int16 | uint16).
 
     windows -> fused normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4) -> gather-form
     overlap average + argmax + nodata (kernel 5).  ``rows=(y0, y1)`` restricts the output to a
     row stripe and only the windows touching it are computed (multi-GPU halo recompute);
     per-pixel sums are formed on one rank in fixed order, so any sharding is bit-identical.
+    ``exchange=(rank, world_size)`` (with ``rows``): the rank computes only ITS share of the window rows
+    (``partition(len(ys), world_size, rank)``) and the window rows its stripe needs from other ranks arrive
+    over NCCL send/recv (``exchange_window_rows``) -- no recomputed halo windows, same bits.
     Returns int8 [y1-y0, W] (numpy unless ``return_tensor``).
     """
     device = "cuda" if device == "gpu" else device
@@ -157,7 +160,8 @@ def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224)
     y0, y1 = rows if rows is not None else (0, H)
     iy_lo, iy_hi = windows_for_rows(ys, win, y0, y1)
     nx = len(xs)
-    wins = [(0, ys[iy], xs[ix]) for iy in range(iy_lo, iy_hi) for ix in range(nx)]
+    own_lo, own_hi = (iy_lo, iy_hi) if exchange is None else partition(len(ys), exchange[1], exchange[0])
+    wins = [(0, ys[iy], xs[ix]) for iy in range(own_lo, own_hi) for ix in range(nx)]
     n_win = len(wins)
     nc = model.num_classes
     win_t = torch.tensor(wins, dtype=torch.int32, device=device).reshape(-1, 3)
@@ -166,13 +170,15 @@ def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224)
     # equal-sized model calls of at most batch_size windows (289 windows, batch 256 -> 145 + 144, not 256 + 33:
     # a small tail call runs the persistent GEMMs at a fraction of a wave)
     n_calls = max(1, -(-n_win // batch_size))
-    per_call = -(-n_win // n_calls)
+    per_call = max(1, -(-n_win // n_calls))
     for s in range(0, n_win, per_call):
         e = min(n_win, s + per_call)
         pre = ops.preprocess(tile.unsqueeze(0), spec, windows=win_t[s:e], win=win, want_f32=False,
                              want_patches=True, fmask=fm, fmask_bits=fmask_bits,
                              masking_strategy=masking_strategy)
         logits[s:e] = model.forward_patches(pre["patches"], want_logits=True)[0]
+    if exchange is not None:
+        logits = exchange_window_rows(logits, ys, win, H, nx, exchange[0], exchange[1])
     nodata_px = None
     if no_data_value is not None or fm is not None:
         # tile-level "any band is nodata" mask from the same kernel (one whole-tile window per 16-aligned block
@@ -196,21 +202,79 @@ def _tile_nodata(tile, spec, H, W, win, ys, xs, fm, fmask_bits, masking_strategy
     wt = torch.tensor(wl, dtype=torch.int32, device=dev)
     m = ops.preprocess(tile.unsqueeze(0), spec, windows=wt, win=win, want_f32=False, want_mask_px=True,
                        fmask=fm, fmask_bits=fmask_bits, masking_strategy=masking_strategy)["mask_px"]
-    full = torch.zeros((H, W), dtype=torch.bool, device=dev)
-    for i, (_, t, l) in enumerate(wl):
-        full[t:t + win, l:l + win] |= m[i]
+    return scatter_window_masks(m, len(ty), len(tx), H, W, win)
+
+
+def scatter_window_masks(m: torch.Tensor, ny: int, nx: int, H: int, W: int, win: int) -> torch.Tensor:
+    """[ny*nx, win, win] masks of the row-major window grid ``window_origins(H, win, win, edge=True)`` x
+    ``window_origins(W, ...)`` -> [H, W], in at most four strided copies (one slice-OR per window was 289
+    tiny launches per 3660^2 tile: milliseconds of host time in a 15 ms step).  The edge-aligned last row /
+    column of windows overlaps its neighbour; the mask is a function of the pixel alone, so overwriting equals OR."""
+    M = m.reshape(ny, nx, win, win)
+    ry, rx = H // win, W // win                     # regular (non edge-aligned) window rows / columns
+    full = torch.empty((H, W), dtype=m.dtype, device=m.device)
+    full[:ry * win, :rx * win] = M[:ry, :rx].permute(0, 2, 1, 3).reshape(ry * win, rx * win)
+    if nx > rx:
+        full[:ry * win, W - win:] = M[:ry, rx].reshape(ry * win, win)
+    if ny > ry:
+        full[H - win:, :rx * win] = M[ry, :rx].permute(1, 0, 2).reshape(win, rx * win)
+        if nx > rx:
+            full[H - win:, W - win:] = M[ry, rx]
     return full
 
 
+def exchange_window_rows(own_logits: torch.Tensor, ys: Sequence[int], win: int, height: int, nx: int,
+                         rank: int, world_size: int) -> torch.Tensor:
+    """Window-row exchange of the sharded sliding window (option ii made exact).
+
+    Rank q computes window rows ``partition(len(ys), world, q)`` (``own_logits`` [rows*nx, nc, win, win]) and
+    stitches output rows ``stripe_rows(height, world, q)``, which are covered by window rows
+    ``windows_for_rows(...)``: the rows it lacks are received from their owners, the rows others lack are sent
+    (``batch_isend_irecv``: NCCL over NVLink on GPUs, gloo in the CPU tests).  What travels are the window
+    LOGITS, not partial sums, so every pixel is still summed on one rank in window order: bit-identical to one GPU,
+    and nobody computes a window twice (halo recompute costs 6 instead of 4 window rows per rank at stride 112
+    on 8 GPUs).  Returns the logits of the needed rows, [(iy_hi - iy_lo) * nx, nc, win, win]."""
+    import torch.distributed as dist
+
+    ny = len(ys)
+    need = [windows_for_rows(ys, win, *stripe_rows(height, world_size, q)) for q in range(world_size)]
+    own = [partition(ny, world_size, q) for q in range(world_size)]
+    (iy_lo, iy_hi), (own_lo, own_hi) = need[rank], own[rank]
+    out = torch.empty(((iy_hi - iy_lo) * nx,) + tuple(own_logits.shape[1:]), dtype=own_logits.dtype,
+                      device=own_logits.device)
+    lo, hi = max(iy_lo, own_lo), min(iy_hi, own_hi)
+    if lo < hi:
+        out[(lo - iy_lo) * nx:(hi - iy_lo) * nx] = own_logits[(lo - own_lo) * nx:(hi - own_lo) * nx]
+    p2p = []
+    for q in range(world_size):
+        if q == rank:
+            continue
+        lo, hi = max(need[q][0], own_lo), min(need[q][1], own_hi)      # rows q lacks and this rank owns
+        if lo < hi:
+            p2p.append(dist.P2POp(dist.isend, own_logits[(lo - own_lo) * nx:(hi - own_lo) * nx], q))
+        lo, hi = max(iy_lo, own[q][0]), min(iy_hi, own[q][1])          # rows this rank lacks and q owns
+        if lo < hi:
+            p2p.append(dist.P2POp(dist.irecv, out[(lo - iy_lo) * nx:(hi - iy_lo) * nx], q))
+    if p2p:
+        for req in dist.batch_isend_irecv(p2p):
+            req.wait()
+    return out
+
+
 @torch.no_grad()
-def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, world_size: int, **kw):
-    """One process per GPU: each rank computes its output row stripe (halo recompute), then the
-    int8 stripes are all-gathered (the only collective on the path).  Returns the full [H, W] map."""
+def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, world_size: int,
+                                     halo_recompute: bool = False, **kw):
+    """One process per GPU: every rank runs the model on its share of the window rows, the rows that straddle a
+    stripe boundary are exchanged over NCCL send/recv, each rank stitches its output row stripe, and the int8
+    stripes are all-gathered.  ``halo_recompute=True`` is the collective-free alternative (every rank recomputes
+    the windows that touch its stripe).  Either way the result is bit-identical to one GPU.  Returns [H, W]."""
     H = hls_tile.shape[1]
     y0, y1 = stripe_rows(H, world_size, rank)
     kw = dict(kw)
     kw["rows"] = (y0, y1)
     kw["return_tensor"] = True
+    if world_size > 1 and not halo_recompute:
+        kw["exchange"] = (rank, world_size)
     local = sliding_window_inference(hls_tile, model, **kw)
     return gather_stripes(local, H, world_size)
 

@@ -67,3 +67,48 @@ def test_gather_world_size_2_gloo():
         p.join(30)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] for r in res)
+
+
+def _exchange_worker(rank, world, port, height, win, stride, nx, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from instageo_b200 import ops
+    ys = ops.window_origins(height, win, stride, True)
+    ny = len(ys)
+    full = torch.arange(ny * nx * 2 * 3 * 3, dtype=torch.float32).reshape(ny * nx, 2, 3, 3)   # "logits" of every window
+    lo, hi = IU.partition(ny, world, rank)
+    got = IU.exchange_window_rows(full[lo * nx:hi * nx].clone(), ys, win, height, nx, rank, world)
+    a, b = IU.windows_for_rows(ys, win, *IU.stripe_rows(height, world, rank))
+    q.put((rank, bool(torch.equal(got, full[a * nx:b * nx])), (a, b), (lo, hi)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height,stride", [(2, 3660, 112), (3, 3660, 224), (4, 1000, 112)])
+def test_window_row_exchange_gloo(world, height, stride):
+    """every rank ends up with exactly the window rows that cover its output stripe, whoever computed them"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() + world * 7 + stride) % 300
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, height, 224, stride, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] for r in res), res
+    # the exchange is not vacuous: some rank needs rows it does not own
+    assert any(r[2][0] < r[3][0] or r[2][1] > r[3][1] for r in res)
+
+
+@pytest.mark.parametrize("H,W,win", [(3660, 3660, 224), (448, 672, 224), (500, 224, 224), (224, 700, 224), (70, 53, 16)])
+def test_scatter_window_masks_equals_per_window_or(H, W, win):
+    ty, tx = ops.window_origins(H, win, win, True), ops.window_origins(W, win, win, True)
+    g = torch.Generator().manual_seed(H + W)
+    pix = torch.rand((H, W), generator=g) < 0.3                      # the mask is a function of the pixel
+    m = torch.stack([pix[t:t + win, l:l + win] for t in ty for l in tx])
+    want = torch.zeros((H, W), dtype=torch.bool)
+    for i, (t, l) in enumerate((t, l) for t in ty for l in tx):
+        want[t:t + win, l:l + win] |= m[i]
+    got = IU.scatter_window_masks(m, len(ty), len(tx), H, W, win)
+    assert torch.equal(got, want) and torch.equal(got, pix)
