@@ -87,3 +87,25 @@ def test_header_cites_reference_for_every_entry_point():
                 "instageo/model/metrics.py:86-108", "instageo/model/metrics.py:209-244", "instageo/model/segmentation.py:117-156",
                 "instageo/model/segmentation.py:202-213", "instageo/data/data_pipeline.py:229-267", "instageo/data/hls_utils.py:359-403"):
         assert ref in src, ref
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """the bench lines kept under profiles/ carry every key the driver's contract names (bench.py docstring / DESIGN §6)"""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_*.json")))
+    assert files, "no bench lines committed"
+    for f in files:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (f, k)
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert d["gpu_launches"] > 0 and d["value"] > 0 and d["vs_baseline"] is None
+        bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert d["n_gpus"] > 1 or not (bad & set(d["clocks"]["reasons"])), (f, d["clocks"])
+    head = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_chips_v1.json")).read().strip().splitlines()[-1])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(head["cpu_baseline"])   # the driver's N = 1 line
+    assert head["roofline"]["bound"] == "tensor" and 0 < head["roofline"]["frac"] < 1
