@@ -223,6 +223,32 @@ def scatter_window_masks(m: torch.Tensor, ny: int, nx: int, H: int, W: int, win:
     return full
 
 
+def exchange_plan(ys: Sequence[int], win: int, height: int, world_size: int) -> list:
+    """Who sends which window rows to whom.  For every rank: ``(need, own, local, sends, recvs)`` with
+    ``need`` = window rows [lo, hi) covering its output stripe, ``own`` = window rows it computes, ``local`` = their
+    intersection (or None), ``sends[q]`` / ``recvs[q]`` = the row range sent to / received from rank q.  Pure function
+    of the geometry, identical on every rank, so the send/recv lists match pairwise without any handshake."""
+    ny = len(ys)
+    need = [windows_for_rows(ys, win, *stripe_rows(height, world_size, q)) for q in range(world_size)]
+    own = [partition(ny, world_size, q) for q in range(world_size)]
+    plan = []
+    for r in range(world_size):
+        lo, hi = max(need[r][0], own[r][0]), min(need[r][1], own[r][1])
+        local = (lo, hi) if lo < hi else None
+        sends, recvs = {}, {}
+        for q in range(world_size):
+            if q == r:
+                continue
+            lo, hi = max(need[q][0], own[r][0]), min(need[q][1], own[r][1])    # rows q lacks and r owns
+            if lo < hi:
+                sends[q] = (lo, hi)
+            lo, hi = max(need[r][0], own[q][0]), min(need[r][1], own[q][1])    # rows r lacks and q owns
+            if lo < hi:
+                recvs[q] = (lo, hi)
+        plan.append((need[r], own[r], local, sends, recvs))
+    return plan
+
+
 def exchange_window_rows(own_logits: torch.Tensor, ys: Sequence[int], win: int, height: int, nx: int,
                          rank: int, world_size: int) -> torch.Tensor:
     """Window-row exchange of the sharded sliding window (option ii made exact).
@@ -236,24 +262,19 @@ def exchange_window_rows(own_logits: torch.Tensor, ys: Sequence[int], win: int, 
     on 8 GPUs).  Returns the logits of the needed rows, [(iy_hi - iy_lo) * nx, nc, win, win]."""
     import torch.distributed as dist
 
-    ny = len(ys)
-    need = [windows_for_rows(ys, win, *stripe_rows(height, world_size, q)) for q in range(world_size)]
-    own = [partition(ny, world_size, q) for q in range(world_size)]
-    (iy_lo, iy_hi), (own_lo, own_hi) = need[rank], own[rank]
+    (iy_lo, iy_hi), (own_lo, own_hi), local, sends, recvs = exchange_plan(ys, win, height, world_size)[rank]
     out = torch.empty(((iy_hi - iy_lo) * nx,) + tuple(own_logits.shape[1:]), dtype=own_logits.dtype,
                       device=own_logits.device)
-    lo, hi = max(iy_lo, own_lo), min(iy_hi, own_hi)
-    if lo < hi:
+    if local is not None:
+        lo, hi = local
         out[(lo - iy_lo) * nx:(hi - iy_lo) * nx] = own_logits[(lo - own_lo) * nx:(hi - own_lo) * nx]
     p2p = []
-    for q in range(world_size):
-        if q == rank:
-            continue
-        lo, hi = max(need[q][0], own_lo), min(need[q][1], own_hi)      # rows q lacks and this rank owns
-        if lo < hi:
+    for q in range(world_size):  # per peer: send first, then receive -- the same order on both sides of a pair
+        if q in sends:
+            lo, hi = sends[q]
             p2p.append(dist.P2POp(dist.isend, own_logits[(lo - own_lo) * nx:(hi - own_lo) * nx], q))
-        lo, hi = max(iy_lo, own[q][0]), min(iy_hi, own[q][1])          # rows this rank lacks and q owns
-        if lo < hi:
+        if q in recvs:
+            lo, hi = recvs[q]
             p2p.append(dist.P2POp(dist.irecv, out[(lo - iy_lo) * nx:(hi - iy_lo) * nx], q))
     if p2p:
         for req in dist.batch_isend_irecv(p2p):

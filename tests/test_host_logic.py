@@ -112,3 +112,27 @@ def test_scatter_window_masks_equals_per_window_or(H, W, win):
         want[t:t + win, l:l + win] |= m[i]
     got = IU.scatter_window_masks(m, len(ty), len(tx), H, W, win)
     assert torch.equal(got, want) and torch.equal(got, pix)
+
+
+@pytest.mark.parametrize("height,stride", [(3660, 112), (3660, 224), (1000, 112), (224, 224), (700, 160), (5000, 64)])
+def test_exchange_plan_is_consistent(height, stride):
+    """for every world size 1..8: each rank's needed rows = local part + disjoint received parts, every send has the
+    matching receive on the peer, nobody sends a row it does not own, and every window row is computed exactly once"""
+    ys = ops.window_origins(height, 224, stride, True)
+    for world in range(1, 9):
+        plan = IU.exchange_plan(ys, 224, height, world)
+        owned = []
+        for r, (need, own, local, sends, recvs) in enumerate(plan):
+            owned += list(range(*own))
+            got = set(range(*local)) if local else set()
+            for q, (lo, hi) in recvs.items():
+                rows = set(range(lo, hi))
+                assert not (rows & got) and plan[q][3][r] == (lo, hi)          # disjoint, and q sends exactly that to r
+                assert plan[q][1][0] <= lo and hi <= plan[q][1][1]             # q owns what it sends
+                got |= rows
+            assert got == set(range(*need)), (world, r)
+            for q, rng in sends.items():
+                assert plan[q][4][r] == rng
+        assert sorted(owned) == list(range(len(ys)))
+        if world == 1:
+            assert plan[0][3] == {} and plan[0][4] == {}
