@@ -6,7 +6,9 @@
 // reshape/permute of the reference costs nothing: Q, K and V tiles are 2-D TMA boxes of that
 // matrix.  Output is written as [B*N, D] (head-major), the exact operand of the proj GEMM.
 //
-// One CTA = 128 query rows of one (batch, head); 2 CTAs per SM.  tcgen05 throughout:
+// PERSISTENT: 2 x (number of SMs) CTAs, each walking work items (one item = 128 query rows of one (batch, head))
+// with its K / V / Q loads and QK^T issue running two KV blocks ahead, across item boundaries (see the comment on
+// the kernel).  tcgen05 throughout:
 //   S_j  = Q K_j^T  : UMMA 128x64x16, both operands K-major (128-byte swizzle), S double-buffered in TMEM
 //   O   += P_j V_j  : UMMA 128x64x16, A = P_j (bf16, written to swizzled smem by the softmax warps),
 //                     B = V_j used MN-major straight from its [kv, 64] tile (no transpose pass)
@@ -18,10 +20,10 @@
 // it by more than 2^8 in the exp2 domain (probabilities stay <= 256, harmless in f32/bf16), and only then
 // is O/L rescaled in TMEM (tcgen05.ld -> multiply -> tcgen05.st, between PV_{j-1} and PV_j).  With
 // attention logits of trained or random-init ViTs that happens in the first block or two; every other
-// block costs 1 FFMA + 1 MUFU + 1/3 FMNMX3 + 1/2 F2F per score.  The first version folded every block's
-// O into 64 register accumulators (64 FFMA + 64 FADD per row and block on top of the exponentials) and ran
-// at 45 % issue utilisation, 2.9x above the MUFU floor (profiles/r01_ncu_attention_before.txt).
+// block costs 1 FFMA + 1 MUFU + 1/3 FMNMX3 + 1/2 F2F per score.
 // In the last KV block only the 16-column groups that contain valid keys are exponentiated.
+// Measurement tooling: tools/attn_ablate.sh (timing ablations, -DATTN_PROFILE in-kernel clock64 phase profile and
+// event trace of CTA 0), tools/attn_profile.py, tools/attn_trace.py, tools/tma_latency.py; findings in DESIGN.md.
 #include "ig_ops.cuh"
 
 namespace attn {
