@@ -142,7 +142,8 @@ def _depth_of(sd) -> int:
 
 
 def block(x: torch.Tensor, sd: dict, pre: str, heads: int) -> torch.Tensor:
-    """timm 1.0.20 ``Block.forward`` (fused-attention branch)."""
+    """timm 1.0.20 ``Block.forward`` (fused-attention branch).  timm is not installed here (parity unpinned against
+    timm itself); tests/test_oracle_block_vs_hf.py checks this function against transformers' ViTMAELayer."""
     B, N, D = x.shape
     hd = D // heads
     h = F.layer_norm(x, (D,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5)
