@@ -131,3 +131,25 @@ def test_stitch_oracle_properties():
     assert np.allclose(avg2[1], 1.5) and (cls2 == 1).all()
     nd = np.zeros((H, W), bool); nd[3, 4] = True
     assert OS.stitch(lg, org, H, W, nd)[1][3, 4] == -1
+
+
+@pytest.mark.parametrize("H,W,win,stride,nc", [(96, 128, 32, 16, 3), (64, 64, 32, 32, 2), (80, 112, 48, 16, 5)])
+def test_stitch_oracle_against_fold_formulation(H, W, win, stride, nc):
+    """The averaging rule has no counterpart in the reference snapshot (parity unpinned).  Independent check
+    of the SPECIFICATION: uniform overlap averaging written as torch.nn.functional.fold(windows) / fold(ones) -- a
+    scatter-add formulation that shares no code with the gather / window-order loop of oracle/stitch.py -- agrees to
+    fp32 summation-order noise, and the class maps agree wherever the top-2 margin exceeds that noise."""
+    import torch.nn.functional as F
+    origins = OS.tile_windows(H, W, win, stride)
+    assert (H - win) % stride == 0 and (W - win) % stride == 0            # regular grid: fold applies
+    rng = np.random.default_rng(H + stride)
+    logits = rng.normal(size=(len(origins), nc, win, win)).astype(np.float32)
+    avg, cls = OS.stitch(logits, origins, H, W)
+    cols = torch.from_numpy(logits).reshape(len(origins), nc * win * win).t().unsqueeze(0)     # [1, nc*win*win, L]
+    summed = F.fold(cols, (H, W), kernel_size=win, stride=stride)[0]
+    count = F.fold(torch.ones_like(cols), (H, W), kernel_size=win, stride=stride)[0]
+    want = (summed / count).numpy()
+    assert np.abs(avg - want).max() < 1e-5
+    top2 = np.sort(want, axis=0)[-2:]
+    safe = (top2[1] - top2[0]) > 1e-4
+    assert safe.mean() > 0.9 and np.array_equal(cls[safe], want.argmax(0).astype(np.int8)[safe])
