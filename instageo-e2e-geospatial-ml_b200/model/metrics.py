@@ -21,7 +21,8 @@ import torch
 
 from .. import _lib
 
-__all__ = ["RunningConfusionMatrix", "RunningAUC", "RunningRegressionMetrics", "segmentation_eval_update"]
+__all__ = ["RunningConfusionMatrix", "RunningAUC", "RunningRegressionMetrics", "segmentation_eval_update",
+           "confusion_summary", "auc_from_histograms"]
 
 _LABEL_DTYPES = {torch.int64: _lib.IG_I64, torch.int32: _lib.IG_I32, torch.uint8: _lib.IG_U8, torch.int8: _lib.IG_I8}
 
@@ -51,6 +52,40 @@ def _safe_div(num: np.ndarray, den: np.ndarray) -> np.ndarray:
     out = np.zeros_like(den)
     np.divide(num, den, out=out, where=den != 0)
     return out
+
+
+def confusion_summary(mat: np.ndarray, total: int) -> dict:
+    """Everything the reference derives from a confusion matrix (metrics.py:110-166), from the k x k integers read
+    back from the device: per-class vectors under ``*_per_class`` and their macro means, plus accuracy."""
+    hits = np.diag(mat)
+    predicted, actual = mat.sum(axis=0), mat.sum(axis=1)            # column sums = tp + fp, row sums = tp + fn
+    per = {"precision": _safe_div(hits, predicted), "recall": _safe_div(hits, actual),
+           "jaccard": _safe_div(hits, predicted + actual - hits)}
+    per["f1"] = _safe_div(2 * per["precision"] * per["recall"], per["precision"] + per["recall"])
+    out = {"accuracy": float("nan") if total == 0 else hits.sum() / total}
+    for name in ("precision", "recall", "f1", "jaccard"):
+        out[name] = per[name].mean()
+        out[name + "_per_class"] = per[name]
+    return out
+
+
+def auc_from_histograms(pos: np.ndarray, neg: np.ndarray) -> np.ndarray:
+    """Per-class one-vs-rest ROC-AUC from the score histograms (metrics.py:246-259): a positive outranks every
+    negative in a lower bin and ties half of those in its own bin.  Accumulated bin by bin in float, like the
+    reference's loop; NaN for a class without positives or without negatives."""
+    aucs = []
+    for p_row, n_row in zip(pos.tolist(), neg.tolist()):
+        n_pos, n_neg = sum(p_row), sum(n_row)
+        if n_pos == 0 or n_neg == 0:
+            aucs.append(float("nan"))
+            continue
+        area, below = 0.0, 0
+        for p_cnt, n_cnt in zip(p_row, n_row):
+            area += p_cnt * below
+            area += 0.5 * p_cnt * n_cnt
+            below += n_cnt
+        aucs.append(area / (n_pos * n_neg))
+    return np.array(aucs)
 
 
 class RunningConfusionMatrix:
@@ -98,41 +133,29 @@ class RunningConfusionMatrix:
         return self._sync()[1]
 
     # -- derived metrics (host arithmetic on k x k integers) --------------------------------------
-    @staticmethod
-    def _parts(mat):
-        tp = np.diag(mat)
-        return tp, mat.sum(axis=0) - tp, mat.sum(axis=1) - tp
+    def _summary(self) -> dict:
+        return confusion_summary(*self._sync())
 
     def accuracy(self) -> float:
-        mat, total = self._sync()
-        return float("nan") if total == 0 else np.diag(mat).sum() / total
+        return self._summary()["accuracy"]
 
     def precision(self) -> np.ndarray:
-        tp, fp, _ = self._parts(self.matrix)
-        return _safe_div(tp, tp + fp)
+        return self._summary()["precision_per_class"]
 
     def recall(self) -> np.ndarray:
-        tp, _, fn = self._parts(self.matrix)
-        return _safe_div(tp, tp + fn)
+        return self._summary()["recall_per_class"]
 
     def f1(self) -> np.ndarray:
-        p, r = self.precision(), self.recall()
-        return _safe_div(2 * p * r, p + r)
+        return self._summary()["f1_per_class"]
 
     def jaccard(self) -> np.ndarray:
-        tp, fp, fn = self._parts(self.matrix)
-        return _safe_div(tp, tp + fp + fn)
+        return self._summary()["jaccard_per_class"]
 
     def compute(self, include_per_class: bool = True) -> dict:
-        mat, total = self._sync()
-        tp, fp, fn = self._parts(mat)
-        prec, rec = _safe_div(tp, tp + fp), _safe_div(tp, tp + fn)
-        f1, jac = _safe_div(2 * prec * rec, prec + rec), _safe_div(tp, tp + fp + fn)
-        out = {"accuracy": float("nan") if total == 0 else tp.sum() / total, "precision": prec.mean(),
-               "recall": rec.mean(), "f1": f1.mean(), "jaccard": jac.mean()}
+        full = self._summary()
+        out = {k: full[k] for k in ("accuracy", "precision", "recall", "f1", "jaccard")}
         if include_per_class:
-            out.update({"precision_per_class": prec.tolist(), "recall_per_class": rec.tolist(),
-                        "f1_per_class": f1.tolist(), "jaccard_per_class": jac.tolist()})
+            out.update({k: v.tolist() for k, v in full.items() if k.endswith("_per_class")})
         return out
 
     def reset(self) -> None:
@@ -190,22 +213,11 @@ class RunningAUC:
     def n_neg(self) -> np.ndarray:
         return self.neg_hist.sum(axis=1)
 
-    def _auc_one_class(self, c: int, pos=None, neg=None) -> float:
-        pos = self.pos_hist if pos is None else pos
-        neg = self.neg_hist if neg is None else neg
-        n_pos, n_neg = int(pos[c].sum()), int(neg[c].sum())
-        if n_pos == 0 or n_neg == 0:
-            return float("nan")
-        auc, cum_neg = 0.0, 0
-        for pc, ncnt in zip(pos[c].tolist(), neg[c].tolist()):  # same accumulation order as the reference
-            auc += pc * cum_neg
-            auc += 0.5 * pc * ncnt
-            cum_neg += ncnt
-        return auc / (n_pos * n_neg)
+    def _auc_one_class(self, c: int) -> float:
+        return float(auc_from_histograms(self.pos_hist[c:c + 1], self.neg_hist[c:c + 1])[0])
 
     def score(self, include_per_class: bool = True) -> dict:
-        pos, neg = self.pos_hist, self.neg_hist
-        per_class = np.array([self._auc_one_class(c, pos, neg) for c in range(self.num_classes)])
+        per_class = auc_from_histograms(self.pos_hist, self.neg_hist)
         macro = np.nanmean(per_class)
         if include_per_class:
             return {"roc_auc_macro": macro, "roc_auc_per_class": per_class.tolist()}

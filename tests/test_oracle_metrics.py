@@ -104,3 +104,39 @@ def test_oracle_equals_live_reference():
         assert all(np.allclose(got[k], want[k], rtol=1e-12) for k in want)
         assert np.allclose(OM.auc_scores(pos, neg, n_pos, n_neg)["roc_auc_per_class"],
                            auc.score()["roc_auc_per_class"], rtol=1e-12, equal_nan=True)
+
+
+def test_host_mirror_derivations_match_reference_golden(gold):
+    """the mirror's host-side arithmetic (what it does with the integers read back from the device), on CPU: pure
+    functions against the fixture frozen from the reference, and the class wrappers over a stubbed read-back"""
+    from instageo_b200.model import metrics as MM
+    for tag in ("nc2", "nc13"):
+        mat, total = gold[f"{tag}_matrix"], int(gold[f"{tag}_total"])
+        s = MM.confusion_summary(mat, total)
+        got = np.array([s["accuracy"], s["precision"], s["recall"], s["f1"], s["jaccard"]])
+        assert np.allclose(got, gold[f"{tag}_scalars"][:5], rtol=1e-12, atol=0)
+        assert np.allclose(s["jaccard_per_class"], gold[f"{tag}_jaccard_per_class"], rtol=1e-12)
+        per = MM.auc_from_histograms(gold[f"{tag}_pos"], gold[f"{tag}_neg"])
+        assert np.allclose(per, gold[f"{tag}_auc_per_class"], rtol=1e-12)
+        cm = object.__new__(MM.RunningConfusionMatrix)            # no device: stub the read-back
+        cm._sync = lambda mat=mat, total=total: (mat, total)
+        want = OM.confusion_metrics(mat, total)
+        out = cm.compute()
+        assert set(out) == set(want) and all(np.allclose(out[k], want[k], rtol=1e-12) for k in want)
+        assert np.allclose(cm.precision(), want["precision_per_class"]) and np.allclose(cm.f1(), want["f1_per_class"])
+        assert np.isclose(cm.accuracy(), want["accuracy"]) and np.allclose(cm.recall(), want["recall_per_class"])
+        assert set(cm.compute(include_per_class=False)) == {"accuracy", "precision", "recall", "f1", "jaccard"}
+        auc = object.__new__(MM.RunningAUC)
+        auc.num_classes = mat.shape[0]
+        saved = MM.RunningAUC.__dict__["pos_hist"], MM.RunningAUC.__dict__["neg_hist"]
+        type(auc).pos_hist = property(lambda self, t=tag: gold[f"{t}_pos"])
+        type(auc).neg_hist = property(lambda self, t=tag: gold[f"{t}_neg"])
+        try:
+            sc = auc.score()
+            assert np.isclose(sc["roc_auc_macro"], gold[f"{tag}_scalars"][5], rtol=1e-12)
+            assert np.isclose(auc._auc_one_class(1), gold[f"{tag}_auc_per_class"][1], rtol=1e-12)
+        finally:
+            MM.RunningAUC.pos_hist, MM.RunningAUC.neg_hist = saved
+    empty = MM.confusion_summary(np.zeros((3, 3), dtype=np.int64), 0)
+    assert np.isnan(empty["accuracy"]) and empty["f1"] == 0.0
+    assert np.isnan(MM.auc_from_histograms(np.zeros((1, 4), np.int64), np.ones((1, 4), np.int64))[0])
