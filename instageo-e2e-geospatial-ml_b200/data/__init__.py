@@ -2,3 +2,4 @@
 from .data_pipeline import (  # noqa: F401
     MASK_DECODING_POS, apply_mask, create_chip, decode_fmask_value, mask_segmentation_map,
 )
+from .geotiff import read_geotiff, write_geotiff  # noqa: F401

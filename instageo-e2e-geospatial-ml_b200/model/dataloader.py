@@ -10,6 +10,8 @@ in ``ig_preprocess`` (sm_100a); results are CUDA tensors (use ``num_workers=0``)
 """
 from __future__ import annotations
 
+import os
+
 from functools import partial
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -128,10 +130,30 @@ def process_raw_chips(raw, mean: Sequence[float], std: Sequence[float], temporal
                           want_mask_elem=want_mask, want_mask_px=want_mask)
 
 
+def get_raster_data(fname, is_label: bool = True, bands: Optional[List[int]] = None,
+                    no_data_value: Optional[int] = -9999, mask_cloud: bool = True, water_mask: bool = False) -> np.ndarray:
+    """instageo/model/dataloader.py:672-704 for a single GeoTIFF: ``rasterio.open(fname).read()`` (all bands,
+    [bands, H, W], file dtype) and the band gather for non-label rasters.  rasterio when importable, else the
+    in-repo TIFF codec (``instageo_b200.data.geotiff``: strips / tiles, none / Deflate / LZW, predictor 2).  The
+    multi-file dict form of the reference (``open_mf_tiff_dataset``, xarray) is out of scope."""
+    if isinstance(fname, dict):
+        raise NotImplementedError("multi-file tile dictionaries (open_mf_tiff_dataset / xarray) are out of scope")
+    try:
+        import rasterio  # type: ignore
+        with rasterio.open(fname) as src:
+            data = src.read()
+    except ImportError:
+        from ..data.geotiff import read_geotiff
+        data = read_geotiff(fname)[0]
+    if (not is_label) and bands:
+        data = data[bands, ...]
+    return data
+
+
 class InstaGeoChipDataset(torch.utils.data.Dataset):
-    """In-memory counterpart of ``InstaGeoDataset`` (dataloader.py:832-906) for already decoded
-    rasters: ``__getitem__`` returns ``((tensor, label), name, nodata_mask)`` like the reference does
-    with ``include_filenames=True``.  File decoding (rasterio) is out of scope."""
+    """Counterpart of ``InstaGeoDataset`` (dataloader.py:832-906): ``chips`` holds decoded rasters
+    [bands, H, W] or GeoTIFF paths (read on access with ``get_raster_data``); ``__getitem__`` returns
+    ``((tensor, label), name, nodata_mask)`` like the reference does with ``include_filenames=True``."""
 
     def __init__(self, chips: Sequence[np.ndarray], names: Sequence[str], preprocess_func, no_data_value,
                  constant_multiplier: float = 1.0, bands: Optional[List[int]] = None,
@@ -148,6 +170,8 @@ class InstaGeoChipDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, i: int):
         data = self.chips[i]
+        if isinstance(data, (str, os.PathLike)):
+            data = get_raster_data(data, is_label=False)
         if self.bands:
             data = data[self.bands, ...]
         arr_x = data * self.constant_multiplier

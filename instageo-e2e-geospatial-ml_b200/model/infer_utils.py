@@ -17,6 +17,8 @@ from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Optional, Sequence
 
 import numpy as np
+from struct import error as struct_error
+
 import torch
 
 from .. import ops
@@ -24,13 +26,24 @@ from .model import PrithviSeg
 
 
 def save_prediction(prediction: np.ndarray, file_name: str, output_folder: str, profile=None) -> None:
-    """instageo/model/infer_utils.py:37-54; GeoTIFF when rasterio is importable, else ``.npy``."""
+    """instageo/model/infer_utils.py:37-54: the prediction as a single-band GeoTIFF carrying the source chip's
+    georeferencing.  rasterio when importable; else the in-repo TIFF codec when the source chip is a TIFF it can
+    read (or a ``profile`` from ``read_geotiff`` is given); else ``.npy``."""
     base = os.path.basename(file_name).replace("chip", "prediction")
     path = os.path.join(output_folder, base)
     try:
         import rasterio  # type: ignore
     except ImportError:
-        np.save(os.path.splitext(path)[0] + ".npy", prediction)
+        from ..data import geotiff
+        if profile is None and os.path.isfile(file_name):
+            try:
+                profile = geotiff.read_geotiff(file_name)[1]
+            except (geotiff.TiffError, OSError, struct_error):
+                profile = None
+        if profile is not None and path.lower().endswith((".tif", ".tiff")):
+            geotiff.write_geotiff(path, prediction, profile)
+        else:
+            np.save(os.path.splitext(path)[0] + ".npy", prediction)
         return
     with rasterio.open(file_name) as src:
         prof = src.profile
