@@ -37,7 +37,9 @@ CROP_MEAN = [494.905781, 815.239594, 924.335066, 2968.881459, 2634.621962, 1739.
 CROP_STD = [284.925432, 357.84876, 575.566823, 896.601013, 951.900334, 921.407808]
 METRIC = "224px 6-band chips/sec/box (device-timed)"
 WORKLOAD = "prithvi_v1_100m_T3_nc13_b64: raw int16 chips -> normalise/mask -> PrithviSeg -> argmax int8"
-CPU_SAMPLE_CHIPS = 2
+CPU_SAMPLE_CHIPS = 8      # chips per CPU step (reference arm and cpu_baseline leg): a bounded sample of the batch of 64
+PARITY_CHIPS = 2          # chips of the TIMED GPU batch that are re-computed by the oracle (bench "parity" key)
+TOL = 2e-2                # north_star: logits within 2e-2 max-abs (bf16 engine vs fp32 reference)
 
 
 def peaks():
@@ -100,24 +102,76 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_step(sd, raw, heads):
-    """Reference CPU path for a chip batch: normalise/mask -> PrithviSeg fp32 -> argmax int8."""
+def stress_init(model, seed: int = 0) -> None:
+    """Random-init weights of the reference's init law (the module's own constructor) plus randomised BatchNorm
+    statistics / affine terms and head biases, so that the class maps are not one constant class (default BatchNorm
+    statistics + zero biases predict almost a single class everywhere: a parity or bit-identity check on such maps
+    proves nothing).  Plain torch, no oracle code: the oracle later runs on THIS model's state_dict."""
+    import torch
+    g = torch.Generator().manual_seed(1000 + seed)
+    with torch.no_grad():
+        for mod in model.segmentation_head.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+            elif isinstance(mod, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)) and mod.bias is not None:
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.05)
+        for blk in model.prithvi_encoder.blocks:
+            for lin in (blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2):
+                lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.02)
+
+
+def cpu_oracle_logits(sd, raw, heads, t=None, mean=None, std=None):
+    """Reference CPU path for a chip batch: normalise/mask -> PrithviSeg fp32 -> logits (torch f32)."""
     import numpy as np
     import torch
     from oracle import preprocess as OP
     from oracle import prithvi as P
-    x = np.stack([OP.preprocess_chip(r, None, 1.0, CROP_MEAN, CROP_STD, T, None)[0] for r in raw])
-    return P.argmax_int8(P.prithvi_seg_forward(torch.from_numpy(x), sd, heads, T))
+    t = T if t is None else t
+    x = np.stack([OP.preprocess_chip(r, None, 1.0, mean or CROP_MEAN, std or CROP_STD, t, None)[0] for r in raw])
+    return P.prithvi_seg_forward(torch.from_numpy(x), sd, heads, t)
 
 
-def cpu_setup():
+def cpu_oracle_step(sd, raw, heads):
+    """... -> argmax int8 (instageo/model/infer_utils.py:99-101)."""
+    from oracle import prithvi as P
+    return P.argmax_int8(cpu_oracle_logits(sd, raw, heads))
+
+
+def cpu_setup(model=None, raw=None):
+    """Weights and chips of the CPU leg.  Inside the GPU bench they are the timed model's own state_dict and the
+    first chips of a timed batch; the stand-alone reference arm draws random-init weights of the same architecture
+    from the oracle's own initialiser."""
     import torch
-    from oracle import preprocess as OP
     from oracle import prithvi as P
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    sd = P.make_state_dict(VARIANT, T, NC, seed=0, stress=True)
-    raw = OP.synth_chips(CPU_SAMPLE_CHIPS, T, seed=1042, nodata=None)
+    if model is None:   # stand-alone reference arm: nothing of the B200 package on this path
+        sd = P.make_state_dict(VARIANT, T, NC, seed=0, stress=True)
+    else:
+        sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items() if v.is_floating_point()}
+    if raw is None:
+        g = torch.Generator(device="cpu").manual_seed(1042)
+        raw = torch.randint(0, 10001, (CPU_SAMPLE_CHIPS, T * 6, 224, 224), generator=g, dtype=torch.int16).numpy()
     return sd, raw, P.VARIANTS[VARIANT][2], torch.get_num_threads()
+
+
+def parity_report(model, sd, heads, raw_np, logits_gpu, amax_gpu, timed_identical):
+    """The oracle against the GPU result for the first chips of a TIMED batch (B = 64 forward_patches path)."""
+    import torch
+    ref = cpu_oracle_logits(sd, raw_np, heads)
+    got = logits_gpu[: len(raw_np)].float().cpu()
+    max_abs = (got - ref).abs().max().item()
+    top2 = ref.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * max(max_abs, 1e-6)     # ties: margin <= 2 eps (SURVEY.md A.7)
+    agree = (amax_gpu[: len(raw_np)].cpu().long() == ref.argmax(1))[safe].float().mean().item() if safe.any() else 0.0
+    hist = torch.bincount(amax_gpu[: len(raw_np)].cpu().long().flatten(), minlength=NC).tolist()
+    ok = bool(max_abs < TOL and agree == 1.0 and safe.float().mean().item() > 0.5 and timed_identical)
+    return {"chips": len(raw_np), "of_timed_batch": BATCH, "max_abs": max_abs, "tol": TOL,
+            "argmax_agree_outside_ties": agree, "excluded": 1.0 - safe.float().mean().item(),
+            "timed_batch_argmax_identical": bool(timed_identical), "class_hist": hist,
+            "oracle": "oracle/ (fp32 CPU restatement of the reference) on the timed model's own state_dict", "ok": ok}
 
 
 def run_reference(args):
@@ -141,18 +195,134 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+FLOOD_MEAN = [0.14245495, 0.13921481, 0.12434631, 0.31420089, 0.20743526, 0.12046503]
+FLOOD_STD = [0.04036231, 0.04186983, 0.05267646, 0.0822221, 0.06834774, 0.05294205]
+TILE_HW = 3660
+
+
+def tile_setup(dev):
+    """BASELINE.json configs[3] inputs: Prithvi-V1-100M T=1 flood head (2 classes, stress-initialised so that the
+    class map is not constant) and a synthetic 3660 x 3660 x 6 int16 HLS tile with a diagonal nodata wedge."""
+    import torch
+    from instageo_b200.model import PrithviSeg
+    torch.manual_seed(0)
+    model = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_v1_100")
+    stress_init(model, seed=1)
+    model = model.to(dev).eval()
+    H = W = TILE_HW
+    g = torch.Generator().manual_seed(1042)
+    tile = torch.randint(0, 10001, (6, H, W), generator=g, dtype=torch.int16)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    tile[:, (yy + xx) < 700] = -9999  # diagonal nodata wedge, like the corner of an HLS tile
+    return model, tile.pin_memory()
+
+
+def tile_kw(stride, tile_batch):
+    # the nodata comparison happens AFTER the constant multiplier (dataloader.py:741, 899 -- SURVEY F10), so the
+    # tile is normalised in raw DN units (statistics x 1e4, multiplier 1.0) to keep -9999 recognisable
+    return dict(window_size=(224, 224), stride=stride, batch_size=tile_batch, mean=[m * 1e4 for m in FLOOD_MEAN],
+                std=[s * 1e4 for s in FLOOD_STD], constant_multiplier=1.0, no_data_value=-9999)
+
+
+def tile_measure(model, pinned_tile, d_tile, rank, world, dev, stride, tile_batch, steps, warmup, families=False):
+    """Time `steps` whole-tile passes (device-resident tile: CUDA events, max over ranks; host tile in / host map out:
+    wall clock, max over ranks).  Returns a dict; `out` = the gathered class map of the last pass (device)."""
+    import torch
+    import torch.distributed as dist
+    from instageo_b200 import _lib, ops
+    from instageo_b200.model import infer_utils as IU
+    kw = tile_kw(stride, tile_batch)
+    H = W = TILE_HW
+    n_win = len(ops.window_origins(H, 224, stride, True)) ** 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return IU.sliding_window_inference_sharded(d_tile, model, rank, world, copy=False, **kw)
+
+    for _ in range(warmup):
+        out = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item() / steps
+    fam = None
+    if families:
+        _lib.profile_enable(True)
+        _lib.profile_report()
+        step()
+        torch.cuda.synchronize()
+        fam = _lib.profile_report()
+        _lib.profile_enable(False)
+    # end to end: pinned host tile in (each rank uploads only the raster rows it touches), host class map out
+    res = torch.empty((H, W), dtype=torch.int8).pin_memory()
+    IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res.copy_(IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw), non_blocking=True)
+        torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return {"ms": ms, "windows": n_win, "windows_per_s": n_win / (ms / 1e3),
+            "e2e_windows_per_s": n_win * steps / dt.item(), "families": fam, "out": out,
+            "same_as_host_path": bool(torch.equal(out.cpu(), res))}
+
+
+def tile_report(model, pinned_tile, rank, world, dev, steps, warmup, tile_batch=256):
+    """The `tile` key of the default bench line: configs[3] at this world size -- stride 112 and 224 -- plus, for
+    N > 1, the bit-identity of the sharded result (window exchange AND halo recompute) against the single-GPU map
+    computed on every rank (the class map has both classes and the nodata wedge: `class_hist`)."""
+    import torch
+    import torch.distributed as dist
+    from instageo_b200.model import infer_utils as IU
+    d_tile = pinned_tile.to(dev)
+    rep = {"workload": "tile_3660x3660x6_int16: sliding windows -> normalise/mask -> PrithviSeg V1-100M T=1 nc=2 "
+                       "(stress init) -> overlap-average stitch -> int8 map; strong scaling over window / stripe shards",
+           "unit": "windows/s", "steps": steps, "warmup": warmup}
+    ok = True
+    for stride in (112, 224):
+        r = tile_measure(model, pinned_tile, d_tile, rank, world, dev, stride, tile_batch, steps, warmup)
+        out = r.pop("out")
+        r.pop("families")
+        entry = {k: r[k] for k in ("ms", "windows", "windows_per_s", "e2e_windows_per_s", "same_as_host_path")}
+        entry["class_hist"] = [int((out == k).sum()) for k in (-1, 0, 1)]
+        if world > 1:
+            kw = tile_kw(stride, tile_batch)
+            single = IU.sliding_window_inference(d_tile, model, return_tensor=True, **kw)
+            halo = IU.sliding_window_inference_sharded(d_tile, model, rank, world, halo_recompute=True, **kw)
+            same = torch.tensor([int(torch.equal(out, single)), int(torch.equal(halo, single))], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            entry["bit_identical_to_single_gpu"] = {"window_exchange": bool(same[0]), "halo_recompute": bool(same[1])}
+            ok = ok and bool(same.min())
+        ok = ok and entry["same_as_host_path"] and min(entry["class_hist"]) > 0
+        rep[f"stride{stride}"] = entry
+    rep["ok"] = ok
+    return rep
+
+
 def run_tile(args):
     """BASELINE.json configs[3]: sliding-window inference over a synthetic 3660 x 3660 x 6 int16 HLS tile with a
-    nodata wedge, Prithvi-V1-100M T=1 flood head (2 classes); ranks split the window rows and the output row stripes,
-    exchange the window rows that straddle a stripe boundary (NCCL send/recv) and all-gather the int8 stripes.  One step = the whole tile; value = windows (224-px chips) per second over all ranks."""
-    import numpy as np
+    nodata wedge, Prithvi-V1-100M T=1 flood head (2 classes); ranks split the windows and the output row stripes,
+    exchange the window logits a stripe needs from other ranks (NCCL send/recv) and all-gather the int8 stripes in
+    place.  One step = the whole tile; value = windows (224-px chips) per second over all ranks."""
     import torch
     import torch.distributed as dist
 
     import instageo_b200
     from instageo_b200 import _lib, ops
-    from instageo_b200.model import PrithviSeg
-    from instageo_b200.model import infer_utils as IU
+    from instageo_b200.model.model import flops_per_chip
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
@@ -161,87 +331,53 @@ def run_tile(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-    mean = [0.14245495, 0.13921481, 0.12434631, 0.31420089, 0.20743526, 0.12046503]
-    std = [0.04036231, 0.04186983, 0.05267646, 0.0822221, 0.06834774, 0.05294205]
-    torch.manual_seed(0)
-    model = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_v1_100").to(dev).eval()
-    H = W = 3660
-    g = torch.Generator().manual_seed(1042)
-    tile = torch.randint(0, 10001, (6, H, W), generator=g, dtype=torch.int16)
-    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
-    tile[:, (yy + xx) < 700] = -9999  # diagonal nodata wedge, like the corner of an HLS tile
-    d_tile = tile.to(dev)
-    # the nodata comparison happens AFTER the constant multiplier (dataloader.py:741, 899 -- SURVEY F10), so the
-    # tile is normalised in raw DN units (statistics x 1e4, multiplier 1.0) to keep -9999 recognisable
-    kw = dict(window_size=(224, 224), stride=args.stride, batch_size=args.tile_batch, mean=[m * 1e4 for m in mean],
-              std=[s * 1e4 for s in std], constant_multiplier=1.0, no_data_value=-9999)
-    n_win_total = len(ops.window_origins(H, 224, args.stride, True)) ** 2
-
-    def step():
-        return IU.sliding_window_inference_sharded(d_tile, model, rank, world, **kw)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        out = step()
+    model, pinned = tile_setup(dev)
+    d_tile = pinned.to(dev)
+    H = W = TILE_HW
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = ms.item()
+    r = tile_measure(model, pinned, d_tile, rank, world, dev, args.stride, args.tile_batch, args.steps, args.warmup,
+                     families=True)
     clocks = sampler.stop() if rank == 0 else None
-    _lib.profile_enable(True)
-    _lib.profile_report()
-    step()
-    torch.cuda.synchronize()
-    fam = _lib.profile_report()
-    _lib.profile_enable(False)
-    # end to end: host tile in (pinned), host class map out
-    pinned = tile.pin_memory()
-    res = torch.empty((H, W), dtype=torch.int8).pin_memory()   # pinned result buffer: D2H at PCIe speed, no staging copy
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res.copy_(IU.sliding_window_inference_sharded(pinned.to(dev, non_blocking=True), model, rank, world, **kw),
-                  non_blocking=True)
-        torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    fam, out, ms, n_win_total = r["families"], r["out"], r["ms"], r["windows"]
     peak_tf, peak_gbs, peak_src = peaks()
+    # dominant family = the tcgen05 GEMMs (encoder linears + head convs); FLOPs of the windows THIS rank computed
+    enc = model.prithvi_encoder
+    fl = flops_per_chip(enc.embed_dim, len(enc.blocks), 1, 2)
+    attn_fl = len(enc.blocks) * 4 * 197 * 197 * enc.embed_dim
+    n_local = -(-n_win_total // world)
+    gemm_ms = fam["gemm_linear"][0] + fam["gemm_conv"][0]
+    gemm_n = fam["gemm_linear"][1] + fam["gemm_conv"][1]
+    achieved = (fl["total"] - attn_fl) * n_local / (gemm_ms / 1e3) / 1e12 if gemm_ms else None
     st_ms, st_n = fam["stitch"]
-    nc = 2
-    stitch_bytes = (n_win_total // world) * nc * 224 * 224 * 4 + 2 * H * W // world
-    out_j = {"metric": METRIC, "value": n_win_total * args.steps / (ms / 1e3), "unit": "chips/s", "n_gpus": world,
-             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+    stitch_bytes = (n_win_total // world) * 2 * 224 * 224 * 4 + 2 * H * W // world
+    fams = {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in fam.items()}
+    if st_ms:
+        fams["stitch"]["achieved_gbs"] = stitch_bytes / (st_ms / max(1, st_n) / 1e3) / 1e9
+        fams["stitch"]["frac_of_hbm_peak"] = fams["stitch"]["achieved_gbs"] / peak_gbs
+    out_j = {"metric": METRIC, "value": r["windows_per_s"], "unit": "chips/s", "n_gpus": world,
+             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
              "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
              "config": {"workload": f"tile_3660x3660x6_int16_stride{args.stride}: sliding windows -> normalise/mask -> "
                                     "PrithviSeg V1-100M T=1 nc=2 -> overlap-average stitch -> int8 map",
                         "windows": n_win_total, "windows_per_call": args.tile_batch,
-                        "parallelism": (f"window rows and output row stripes x{world}: boundary window rows exchanged by NCCL send/recv "
-                                        "(no recompute), int8 stripe all-gather; bit-identical to 1 GPU") if world > 1 else "single GPU",
+                        "parallelism": (f"windows and output row stripes x{world}: window logits a stripe needs from other ranks "
+                                        "exchanged by NCCL send/recv (no recompute), in-place int8 stripe all-gather; "
+                                        "bit-identical to 1 GPU") if world > 1 else "single GPU",
                         "l2": "tile 80 MB + window logits 116-411 MB + >1 GB activations per step, larger than L2"},
              "clocks": clocks,
-             "e2e": {"value": n_win_total * args.steps / dt.item(), "unit": "chips/s", "h2d_bytes_per_step": 6 * H * W * 2,
-                     "d2h_bytes_per_step": H * W, "api": "instageo_b200.model.infer_utils.sliding_window_inference_sharded"},
+             "e2e": {"value": r["e2e_windows_per_s"], "unit": "chips/s",
+                     "h2d_bytes_per_step": 6 * H * W * 2 // world, "d2h_bytes_per_step": H * W,
+                     "api": "instageo_b200.model.infer_utils.sliding_window_inference_sharded (pinned host tile in, host map out)"},
              "gpu_launches": int(sum(v[1] for v in fam.values())) * args.steps,
-             "roofline": {"kernel": "stitch kernel (kernel 5)", "bound": "hbm", "achieved": stitch_bytes / (st_ms / max(1, st_n) / 1e3) / 1e9 if st_ms else None,
-                          "peak": peak_gbs, "unit": "GB/s", "frac": (stitch_bytes / (st_ms / max(1, st_n) / 1e3) / 1e9 / peak_gbs) if st_ms else None,
-                          "traffic": None, "peak_source": peak_src},
-             "kernel_families": {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in fam.items()},
-             "class_hist": [int((res == k).sum()) for k in (-1, 0, 1)]}
+             "roofline": {"kernel": "gemm_kernel<EPI> (tcgen05 GEMM: encoder linears + head implicit-GEMM convs, T=1 shapes)",
+                          "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                          "frac": achieved / peak_tf if achieved else None, "traffic": None, "peak_source": peak_src,
+                          "avg_launch_ms": gemm_ms / max(1, gemm_n)},
+             "kernel_families": fams,
+             "same_as_host_path": r["same_as_host_path"],
+             "class_hist": [int((out == k).sum()) for k in (-1, 0, 1)]}
     if rank == 0:
         print(json.dumps(out_j))
     if world > 1:
@@ -396,6 +532,7 @@ def main():
     ap.add_argument("--chips", type=int, default=0, help="chipset_100k: total chips (default 12500 per GPU)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tile", action="store_true", help="default workload: skip the configs[3] tile section")
     ap.add_argument("--workload", default="chips_v1_100m_t3", choices=sorted(WORKLOADS) + ["tile_3660", "chipset_100k"])
     ap.add_argument("--stride", type=int, default=224, help="tile_3660: sliding-window stride")
     ap.add_argument("--tile-batch", type=int, default=256, help="tile_3660: windows per model call (at most)")
@@ -433,7 +570,9 @@ def main():
     _lib.load()
 
     torch.manual_seed(0)
-    model = PrithviSeg(temporal_step=T, num_classes=NC, load_pretrained_weights=False, variant=VARIANT).to(dev).eval()
+    model = PrithviSeg(temporal_step=T, num_classes=NC, load_pretrained_weights=False, variant=VARIANT)
+    stress_init(model)
+    model = model.to(dev).eval()
     spec = ops.PreprocessSpec(CROP_MEAN, CROP_STD, T, None, 1.0, None, dev)
     g = torch.Generator(device="cpu").manual_seed(1042 + rank)
     n_rot = 4  # rotating input batches: 4 x 115.6 MB > 126 MB L2
@@ -464,6 +603,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     launches_per_step = 1 + model.launches_per_forward() - 1  # preprocess + forward (no patchify: bf16 rows in)
+    graph = model.graph_status()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -471,7 +611,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step(i)
+        last_amax = step(i)
     if world > 1:
         torch.cuda.current_stream(dev).wait_stream(gather_stream)  # the last gather is inside the timed region
     e1.record()
@@ -538,23 +678,50 @@ def main():
            "dtype": "bf16", "data": "synthetic",
            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                       "parallelism": f"chip-sharded x{world}, int8 mask all-gather" if world > 1 else "single GPU",
-                      "l2": "4 rotating input batches (462 MB int16) + >1 GB of activations per step, larger than the 126 MB L2"},
+                      "l2": "4 rotating input batches (462 MB int16) + >1 GB of activations per step, larger than the 126 MB L2",
+                      "weights": "random init (reference init law) + randomised BatchNorm statistics / biases (bench.stress_init)"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-           "kernel_families": families}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sd, raw, heads, cores = cpu_setup()
-        cpu_oracle_step(sd, raw[:1], heads)
-        t0, n = time.perf_counter(), 0
-        while n < 3 and (n == 0 or time.perf_counter() - t0 < 12):
-            cpu_oracle_step(sd, raw, heads)
-            n += 1
-        v = CPU_SAMPLE_CHIPS * n / (time.perf_counter() - t0)
-        out["cpu_baseline"] = {"value": v, "unit": "chips/s", "cores": cores, "kind": "port",
-                               "sample": f"{n} x {CPU_SAMPLE_CHIPS} chips of the same workload through oracle/ (reference CPU path, fp32)"}
+           "kernel_families": families,
+           "forward_path": {"cuda_graph_replay": bool(graph["last_forward_was_graph"]), "kernels_per_graph": graph["kernels_in_graph"],
+                            "note": graph["note"]}}
+
+    # ---- parity of the TIMED configuration: the argmax of the last timed step's batch (B = 64 forward_patches path)
+    # must be reproduced by one more call on the same batch (which also returns the logits), and the first chips of
+    # that batch are re-computed by the fp32 CPU oracle on this model's own weights
+    idx = (args.steps - 1) % n_rot
+    pre = ops.preprocess(d_raws[idx], spec, want_f32=False, want_patches=True)
+    l_par, a_par = model.forward_patches(pre["patches"], want_logits=True, want_argmax=True)
+    timed_identical = bool(torch.equal(a_par, last_amax))
+
+    # ---- configs[3] (sliding-window tile) at this world size: throughput + N-GPU bit-identity
+    tile = None
+    if args.workload == "chips_v1_100m_t3" and not args.no_tile:
+        del pipe, pinned
+        t_model, t_pinned = tile_setup(dev)
+        tile = tile_report(t_model, t_pinned, rank, world, dev, steps=max(2, min(5, args.steps)), warmup=2)
+        out["tile"] = tile
+        del t_model, t_pinned
+
+    ok = True
     if rank == 0:
+        sd, raw_cpu, heads, cores = cpu_setup(model, raws[idx][:CPU_SAMPLE_CHIPS].numpy())
+        out["parity"] = parity_report(model, sd, heads, raw_cpu[:PARITY_CHIPS], l_par, a_par, timed_identical)
+        ok = out["parity"]["ok"] and (tile is None or tile["ok"])
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_oracle_step(sd, raw_cpu[:1], heads)
+            t0, n = time.perf_counter(), 0
+            while n < 3 and (n == 0 or time.perf_counter() - t0 < 12):
+                cpu_oracle_step(sd, raw_cpu, heads)
+                n += 1
+            v = CPU_SAMPLE_CHIPS * n / (time.perf_counter() - t0)
+            out["cpu_baseline"] = {"value": v, "unit": "chips/s", "cores": cores, "kind": "port",
+                                   "sample": f"{n} x {CPU_SAMPLE_CHIPS} chips of the timed batch (of {BATCH}) through oracle/ "
+                                             "(reference CPU path, fp32, all host threads)"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -12,8 +12,10 @@
  *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
  *   - every data pointer is a DEVICE pointer owned by the caller (PyTorch allocates);
  *     the library owns only the opaque ig_model (packed bf16 weights).
- *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden
- *     streams, no device-wide synchronisation in the forward path (CUDA-graph capturable).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing executes
+ *     on any other stream, no device-wide synchronisation in the forward path.  ig_model_forward
+ *     is CUDA-graph capturable by the caller; left alone it replays its own captured graph
+ *     (see "Forward schedule cache" below).
  *   - return 0 on success, negative IG_E* on failure; ig_last_error() gives a
  *     thread-local message.  Never aborts, never prints.
  *   - no CPU fallback: on a device that is not compute capability 10.x every compute
@@ -90,6 +92,18 @@ int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_src_bands, in
                   int masking_strategy, float* out_f32, void* out_patch, uint8_t* mask_elem,
                   uint8_t* mask_px, void* stream);
 
+/* Tile-level nodata map for the sliding-window path: out[y - y0, x] = 1 when ANY selected band /
+ * timestep of tile pixel (y, x) is nodata by the element test of ig_preprocess (Fmask-flagged
+ * pixels replaced by no_data_value before scaling, float64(raw) * constant_multiplier ==
+ * no_data_value; instageo/model/dataloader.py:741, :899), for rows [y0, y1) of ONE image
+ * raw [n_src_bands, H, W] (strides in elements, pixel stride 1; W need not be a multiple of 8).
+ * fmask [T, H, W] uint8 or NULL.  out [y1 - y0, W] uint8.  This is the nodata_px input of ig_stitch. */
+int ig_nodata_map(const void* raw, int raw_dtype, int n_src_bands, int H, int W, int64_t band_stride,
+                  int64_t row_stride, const int32_t* band_idx, int T, int C,
+                  double constant_multiplier, int has_nodata, double no_data_value,
+                  const uint8_t* fmask, uint32_t fmask_bits, int masking_strategy, int y0, int y1,
+                  uint8_t* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Kernel 5: overlap-averaging stitch of sliding-window logits (specification: SURVEY.md
  * Appendix A.6; the reference snapshot only has the window grid, dataloader.py:655-664, the
@@ -101,6 +115,8 @@ int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_src_bands, in
  * [win_base, win_base + n_win) must not cover rows [y0, y1)).
  * Output rows [y0, y1) of the H x W tile: class_map [y1-y0, W] int8, optional avg
  * [nc, y1-y0, W] float32, optional class histogram hist [nc+1] uint64 (last = nodata).
+ * nodata_px [y1-y0, W] uint8 or NULL: the SAME rows [y0, y1) as the outputs (ig_nodata_map writes
+ * exactly this); non-zero pixels become nodata_class.
  */
 int ig_stitch(const float* win_logits, int n_win, int win_base, int nc, int win,
               const int32_t* ys, int ny, const int32_t* xs, int nx, int H, int W, int y0, int y1,
@@ -147,11 +163,33 @@ int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* 
  * (logits never stored).  num_classes >= 2. */
 int ig_model_predict_proba(ig_model* m, const void* x, int x_dtype, int batch, float* prob_pos,
                            void* workspace, size_t workspace_bytes, void* stream);
-/* number of kernel launches one ig_model_forward enqueues (for bench accounting) */
+/* number of kernels one ig_model_forward runs (f32 entry; the bf16 tubelet-row entry runs one
+ * less: no patchify), for bench accounting */
 int ig_model_launches_per_forward(const ig_model* m);
+/* Forward schedule cache.  The model keeps, per (batch, workspace address), the GEMM plans with
+ * their TMA descriptors, the fact that the zero borders of the head buffers inside that workspace
+ * have been cleared, and -- for the bf16 tubelet-row entry -- an instantiated CUDA graph of the
+ * whole forward (one cudaGraphLaunch per call; x / logits / argmax / prob pointers that change
+ * between calls are patched into two kernel nodes).  The workspace contents between forwards
+ * therefore belong to the library: if anything else writes into it, or it is freed and the
+ * address reused, call ig_model_reset_cache.  Set IG_NO_GRAPH=1 in the environment to force the
+ * eager path (identical kernels, launched one by one). */
+int ig_model_reset_cache(ig_model* m);
+/* returns 1 while graph replay is enabled, 0 once a CUDA graph API call failed (the forward then
+ * stays on the eager path; `note` receives the reason).  *last_forward_was_graph: 1 if the last
+ * forward was a graph launch; *kernels_in_graph: kernel nodes of the last captured graph. */
+int ig_model_graph_status(const ig_model* m, int* last_forward_was_graph, int* kernels_in_graph,
+                          char* note, size_t note_bytes);
 /* debug / parity taps: copy an intermediate activation of the LAST forward as float32.
- * name: "embed", "block<i>", "tokens", "convt<i>", "stage<i>".  dst layouts follow the
- * oracle taps ([B,N,D] for tokens, [B,C,H,W] for head maps). */
+ *   head maps  "feat" (pre-head features), "convt<i>", "stage<i>": [B, C, H, W], read from the
+ *              workspace;
+ *   encoder    "x" (residual stream after the last block, from the workspace), and -- only while
+ *              a tap buffer is attached -- "embed" (after patch embed + pos + cls), "block<i>"
+ *              (after block i), "tokens" (after the final LayerNorm): [B, N, D].
+ * ig_model_set_tap_buffer attaches a caller-owned float32 device buffer of at least
+ * (depth + 2) * B * N * D elements that every following forward fills (eager path, extra
+ * device-to-device copies: test use only); NULL detaches it. */
+int ig_model_set_tap_buffer(ig_model* m, float* buf, size_t elems);
 int ig_model_debug_tap(ig_model* m, const char* name, int batch, void* workspace, float* dst,
                        size_t dst_elems, void* stream);
 int ig_model_destroy(ig_model* m);

@@ -38,6 +38,7 @@ SIGNATURES = {
     "ig_last_error": (C.c_char_p, []),
     "ig_preprocess": (_I, [_P, _I, _I, _I, _I, _I, _I64, _I64, _I64, _P, _I, _I, _P, _I, _I, _D, _P, _P, _I, _D,
                            _P, _U32, _I, _P, _P, _P, _P, _P]),
+    "ig_nodata_map": (_I, [_P, _I, _I, _I, _I, _I64, _I64, _P, _I, _I, _D, _I, _D, _P, _U32, _I, _I, _I, _P, _P]),
     "ig_stitch": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     "ig_model_create": (_I, [C.POINTER(ModelCfg), C.POINTER(_P)]),
     "ig_model_load_weight": (_I, [_P, C.c_char_p, _P, C.POINTER(_I64), _I, _P]),
@@ -47,6 +48,9 @@ SIGNATURES = {
     "ig_model_predict_proba": (_I, [_P, _P, _I, _I, _P, _P, _SZ, _P]),
     "ig_model_launches_per_forward": (_I, [_P]),
     "ig_model_debug_tap": (_I, [_P, C.c_char_p, _I, _P, _P, _SZ, _P]),
+    "ig_model_set_tap_buffer": (_I, [_P, _P, _SZ]),
+    "ig_model_reset_cache": (_I, [_P]),
+    "ig_model_graph_status": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.c_char_p, _SZ]),
     "ig_model_destroy": (_I, [_P]),
     "ig_linear": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ig_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
@@ -91,10 +95,28 @@ def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def current_stream() -> int:
+def current_stream(device=None) -> int:
+    """cudaStream_t of torch's current stream ON ``device`` (a tensor's device, not the current device: launching
+    device-1 pointers on device 0's stream is an illegal access)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(t):
+    """Context manager: make ``t``'s device current for the duration of a C-ABI call (the library launches on the
+    current device)."""
+    import torch
+
+    return torch.cuda.device(t.device)
+
+
+def call(name: str, device, *args) -> None:
+    """``ig_<name>(*args, stream)`` with ``device`` current and torch's current stream on it."""
+    import torch
+
+    with torch.cuda.device(device):
+        check(getattr(load(), name)(*args, current_stream(device)))
 
 
 PROF_FAMILIES = ["preprocess", "stitch", "gemm_linear", "gemm_conv", "attention", "layernorm", "other"]

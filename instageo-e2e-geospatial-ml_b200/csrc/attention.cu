@@ -575,18 +575,24 @@ extern "C" int ig_attention_profile(unsigned long long* out16) {
 #endif
 
 namespace ops {
-int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t st) {
+// The two TMA descriptors of a launch depend only on (qkv pointer, B, N, heads): the model engine encodes them once
+// per (batch, workspace) plan instead of once per block per forward.
+int attention_maps(const void* qkv, int B, int N, int heads, CUtensorMap* tmq, CUtensorMap* tmkv) {
   IG_REQUIRE(B >= 1 && N >= 1 && heads >= 1, IG_ESHAPE, "attention: bad shape B=%d N=%d heads=%d", B, N, heads);
   const int D = heads * attn::HD;
-  static bool configured = false;
-  if (!configured) {
+  IG_TRY(ig_make_tmap_bf16(tmq, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BQ, 64));
+  IG_TRY(ig_make_tmap_bf16(tmkv, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BKV, 64));
+  return IG_OK;
+}
+int attention_planned(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* out, int B, int N, int heads,
+                      cudaStream_t st) {
+  const int D = heads * attn::HD;
+  static IgPerDevice configured = {};
+  if (!configured.get()) {
     IG_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     attn::SMEM_TOTAL));
-    configured = true;
+    configured.set(1);
   }
-  CUtensorMap tmq, tmkv;
-  IG_TRY(ig_make_tmap_bf16(&tmq, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BQ, 64));
-  IG_TRY(ig_make_tmap_bf16(&tmkv, qkv, static_cast<uint64_t>(B) * N, 3 * D, 3 * D, attn::BKV, 64));
   const int nqt = (N + attn::BQ - 1) / attn::BQ;
   IG_REQUIRE(static_cast<int64_t>(nqt) * heads * B < (1ll << 31), IG_ESHAPE, "attention: too many work items");
   const int total_items = nqt * heads * B;
@@ -596,6 +602,11 @@ int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t 
                                                                       nqt, heads, total_items);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
+}
+int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t st) {
+  CUtensorMap tmq, tmkv;
+  IG_TRY(attention_maps(qkv, B, N, heads, &tmq, &tmkv));
+  return attention_planned(tmq, tmkv, out, B, N, heads, st);
 }
 }  // namespace ops
 

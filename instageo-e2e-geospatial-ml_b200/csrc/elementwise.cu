@@ -189,6 +189,19 @@ int cvt_bf16(const float* s, void* d, int64_t n, cudaStream_t st) {
   return IG_OK;
 }
 
+__global__ void cvt_f32_kernel(const __nv_bfloat16* s, float* d, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+int cvt_f32(const void* s, float* d, int64_t n, cudaStream_t st) {
+  if (n <= 0) return IG_OK;
+  cvt_f32_kernel<<<static_cast<unsigned>((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(s), d, n);
+  IG_CUDA_OK(cudaGetLastError());
+  return IG_OK;
+}
+
 // transposed = 1: src [Cin][Cout][3][3] (ConvTranspose2d); 0: src [Cout][Cin][3][3] (Conv2d)
 // dst [Cout][9*Cin], k = (ky*3+kx)*Cin + perm(cin); permT > 1: cin = d*permT + t -> t*(Cin/permT) + d
 __global__ void conv_w_kernel(const float* s, __nv_bfloat16* d, int Cin, int Cout, int transposed, int permT) {

@@ -525,11 +525,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int EPI>
 static int launch_epi(const Plan& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static IgPerDevice configured = {};
+  if (!configured.get()) {
     IG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     SMEM_TOTAL));
-    configured = true;
+    configured.set(1);
   }
   const int total = p.args.num_m_tiles * p.args.num_n_tiles * p.args.num_phases;
   if (total <= 0) return IG_OK;

@@ -38,6 +38,15 @@ int ig_check_device();  // IG_OK if current device is sm_100, else IG_EARCH (+me
 
 int ig_num_sms();
 
+// cudaFuncSetAttribute is a PER-DEVICE setting: a process that drives several GPUs (one model per device, or the
+// test suite's cuda:1 cases) must configure every kernel once on each of them.  get() = the largest setting made so
+// far on the current device for this call site (0 = none); the caller records a new one with set().
+struct IgPerDevice {
+  int v[64];
+  int get() const;
+  void set(int value);
+};
+
 // TMA descriptor for a row-major 2-D bf16 matrix [rows, cols] (cols contiguous), box
 // [box_rows, 64 cols], 128-byte swizzle.  row_pitch in elements.
 int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
@@ -53,6 +62,7 @@ int ig_make_tmap_nd(CUtensorMap* map, int dtype, const void* base, int rank, con
 namespace ig {
 enum ProfCat { PROF_PREPROCESS = 0, PROF_STITCH, PROF_GEMM_LINEAR, PROF_GEMM_CONV, PROF_ATTENTION,
                PROF_LAYERNORM, PROF_MISC, PROF_COUNT };
+bool prof_enabled();
 void prof_begin(int cat, cudaStream_t st);
 void prof_end(int cat, cudaStream_t st);
 struct ProfScope {

@@ -16,4 +16,9 @@ int repack_head1x1(const float* w, const float* b, float* wd, float* bd, int nc,
 int unpad_to_nchw(const void* buf, float* dst, int B, int Hp, int Wp, int C, int guard, int permT, cudaStream_t st);
 // fused attention over qkv bf16 [B*N, 3*D] -> out bf16 [B*N, D] (attention.cu)
 int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t st);
+int attention_maps(const void* qkv, int B, int N, int heads, CUtensorMap* tmq, CUtensorMap* tmkv);
+int attention_planned(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* out, int B, int N, int heads,
+                      cudaStream_t st);
+// bf16 -> f32 copy (parity taps)
+int cvt_f32(const void* s, float* d, int64_t n, cudaStream_t st);
 }  // namespace ops

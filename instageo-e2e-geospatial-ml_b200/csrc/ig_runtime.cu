@@ -49,6 +49,17 @@ int ig_num_sms() {
   return sms;
 }
 
+int IgPerDevice::get() const {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return __atomic_load_n(&v[dev], __ATOMIC_ACQUIRE);
+}
+void IgPerDevice::set(int value) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  __atomic_store_n(&v[dev], value, __ATOMIC_RELEASE);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -130,6 +141,7 @@ std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_open[ig::PROF_COUNT];
 }  // namespace
 
+bool ig::prof_enabled() { return g_prof_on; }
 void ig::prof_begin(int cat, cudaStream_t st) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -313,10 +313,10 @@ __global__ void __launch_bounds__(THREADS) auc_scores_kernel(const T* __restrict
 
 template <int NC>
 int launch_seg(const SegArgs& a, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static IgPerDevice configured = {};
+  if (!configured.get()) {
     IG_CUDA_OK(cudaFuncSetAttribute(seg_metrics_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured.set(1);
   }
   const long long quads = a.n_img * (a.hw >> 2);
   if (quads == 0) return IG_OK;
@@ -490,11 +490,11 @@ extern "C" int ig_auc_update(const void* scores, int score_dtype, int64_t n, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2ull * num_classes * n_bins * 4;
   const int use_smem = smem <= 96 * 1024;
-  static bool configured = false;
-  if (!configured) {
+  static IgPerDevice configured = {};
+  if (!configured.get()) {
     IG_CUDA_OK(cudaFuncSetAttribute(auc_scores_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     IG_CUDA_OK(cudaFuncSetAttribute(auc_scores_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
+    configured.set(1);
   }
   long long blocks = (n + THREADS - 1) / THREADS;
   if (blocks > 2ll * ig_num_sms()) blocks = 2ll * ig_num_sms();

@@ -14,6 +14,7 @@
 //   hid     bf16 [B*N, 4D]            GELU(fc1) = A operand of fc2
 //   head    bf16 padded-flat NHWC     [guard + B*(H+2)*(W+2) + guard, C] per stage, zero border;
 //                                     stage-0 channels stored t*D + d (weights permuted to match)
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -52,6 +53,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+struct ig_fwd_plan;
+
 struct ig_model {
   ig_model_cfg cfg;
   int D, L, heads, T, nc, g, ntok, K0;
@@ -66,6 +69,19 @@ struct ig_model {
   std::vector<LayerW> layers;
   StageW st[4];
   float *w1_raw, *b1_raw, *w1, *b1;
+  // forward schedule cache (see "Forward schedule" below)
+  std::vector<ig_fwd_plan*> plans;
+  uint64_t use_ctr;
+  char* ring_ws;      // (workspace, batch) whose head-buffer borders are currently zero
+  int ring_batch;
+  float* tap_buf;     // caller-owned [(L + 2), B, N, D] f32 or null (ig_model_set_tap_buffer)
+  size_t tap_elems;
+  int tap_batch;
+  bool graphs_ok;
+  cudaStream_t cap_stream;
+  int last_path;      // 1 = the last forward was a graph launch
+  int graph_kernels;  // kernel nodes of the most recently captured graph
+  char graph_note[256];
 };
 
 namespace {
@@ -186,6 +202,17 @@ extern "C" int ig_model_create(const ig_model_cfg* cfg, ig_model** out) {
   m->K0 = cfg->in_chans * 256;
   for (int i = 0; i < 5; ++i) m->dims[i] = cfg->head_dims[i];
   m->finalized = false;
+  m->use_ctr = 0;
+  m->ring_ws = nullptr;
+  m->ring_batch = 0;
+  m->tap_buf = nullptr;
+  m->tap_elems = 0;
+  m->tap_batch = 0;
+  m->graphs_ok = true;
+  m->cap_stream = nullptr;
+  m->last_path = 0;
+  m->graph_kernels = 0;
+  m->graph_note[0] = 0;
   cudaGetDevice(&m->device);
   const int D = m->D;
   int rc = IG_OK;
@@ -247,6 +274,8 @@ extern "C" int ig_model_create(const ig_model_cfg* cfg, ig_model** out) {
 
 extern "C" int ig_model_destroy(ig_model* m) {
   if (!m) return IG_OK;
+  ig_model_reset_cache(m);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
   return IG_OK;
@@ -357,8 +386,9 @@ extern "C" size_t ig_model_workspace_bytes(const ig_model* m, int batch) {
 
 extern "C" int ig_model_launches_per_forward(const ig_model* m) {
   if (!m) return 0;
-  // patchify + cls + patch-embed + 7 per block + final norm + 5 border clears + 8 head GEMMs
-  return 3 + 7 * m->L + 1 + 5 + 8;
+  // patchify (f32 entry only) + cls + patch-embed + 7 per block + final norm + 8 head GEMMs; the 5 border clears
+  // run once per (batch, workspace) layout, not per forward
+  return 3 + 7 * m->L + 1 + 8;
 }
 
 namespace {
@@ -426,6 +456,408 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------------
+// Forward schedule.  Everything that depends only on (batch, workspace address) -- ~30 + 4 L GEMM plans with their
+// TMA descriptors, the attention descriptors -- is built ONCE per (batch, workspace) and kept in the model
+// (FwdPlan); the production entry (bf16 tubelet rows in, no feature tap) is additionally captured into a CUDA
+// graph per plan, so a steady-state forward is one cudaGraphLaunch.  Before this, every forward re-encoded ~120
+// tensor maps on the host and issued ~108 launches: 17.02 ms per step for 16.52 ms of kernels (BENCH_r01).
+// Caller pointers that may change between forwards (x, logits, argmax, prob) live in the parameters of exactly
+// two kernel nodes (patch-embed GEMM, fused final conv); they are patched with cudaGraphExecKernelNodeSetParams.
+
+namespace {
+
+struct FwdIO {
+  const void* x;
+  int x_dtype;
+  float* logits;
+  int8_t* argmax;
+  float* prob1;
+  float* feats;
+};
+
+struct GraphEntry {
+  unsigned flags;  // bit 0 logits, bit 1 argmax, bit 2 prob1
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  cudaGraphNode_t n_patch, n_final;
+  FwdIO io;  // pointers currently baked into the executable graph
+};
+
+}  // namespace
+
+struct ig_fwd_plan {
+  int batch;
+  char* ws;
+  Layout l;
+  gemm::Plan patch;        // A = ws + l.patches (f32 entry: rows written by patchify)
+  gemm::Plan patch_ext;    // A = caller's tubelet rows (bf16 entry), re-encoded when the pointer changes
+  const void* patch_ext_src;
+  std::vector<gemm::Plan> enc;  // qkv, proj, fc1, fc2 per block
+  CUtensorMap tmq, tmkv;
+  gemm::Plan convt[4], conv[3], fin;
+  std::vector<GraphEntry> graphs;
+  uint64_t last_use;
+};
+
+namespace {
+
+const int MAX_PLANS = 8;
+
+void destroy_plan(ig_fwd_plan* fp) {
+  for (GraphEntry& g : fp->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  delete fp;
+}
+
+int build_plan(ig_model* m, int batch, char* ws, ig_fwd_plan** out) {
+  ig_fwd_plan* fp = new ig_fwd_plan();
+  fp->batch = batch;
+  fp->ws = ws;
+  fp->l = make_layout(m, batch);
+  fp->patch_ext_src = nullptr;
+  fp->last_use = 0;
+  const Layout& l = fp->l;
+  const int B = batch, D = m->D, T = m->T, g = m->g, N = m->ntok;
+  const int M = B * N, MP = B * T * g * g;
+  float* xres = reinterpret_cast<float*>(ws + l.x);
+  bf16* xn = reinterpret_cast<bf16*>(ws + l.xn);
+  bf16* qkv = reinterpret_cast<bf16*>(ws + l.qkv);
+  bf16* att = reinterpret_cast<bf16*>(ws + l.att);
+  bf16* hid = reinterpret_cast<bf16*>(ws + l.hid);
+  int rc = IG_OK;
+#define PLAN_TRY(expr) do { if (rc == IG_OK) rc = (expr); } while (0)
+  PLAN_TRY(gemm::plan_linear(&fp->patch, gemm::EPI_PATCH, ws + l.patches, m->K0, m->pe_w, MP, D, m->K0));
+  if (rc == IG_OK) {
+    gemm::Args& a = fp->patch.args;
+    a.bias = m->pe_b;
+    a.pos = m->pos;
+    a.tok_per_img = T * g * g;
+    a.ntok = N;
+    a.out = xres;
+    fp->patch_ext = fp->patch;
+  }
+  fp->enc.resize(static_cast<size_t>(4) * m->L);
+  for (int i = 0; i < m->L && rc == IG_OK; ++i) {
+    const LayerW& w = m->layers[i];
+    gemm::Plan* p = &fp->enc[static_cast<size_t>(4) * i];
+    PLAN_TRY(gemm::plan_linear(&p[0], gemm::EPI_BF16, xn, D, w.qkv_w, M, 3 * D, D));
+    p[0].args.bias = w.qkv_b;
+    p[0].args.out = qkv;
+    PLAN_TRY(gemm::plan_linear(&p[1], gemm::EPI_RESID, att, D, w.proj_w, M, D, D));
+    p[1].args.bias = w.proj_b;
+    p[1].args.resid = xres;
+    p[1].args.out = xres;
+    PLAN_TRY(gemm::plan_linear(&p[2], gemm::EPI_BF16, xn, D, w.fc1_w, M, 4 * D, D));
+    p[2].args.bias = w.fc1_b;
+    p[2].args.act = 1;
+    p[2].args.out = hid;
+    PLAN_TRY(gemm::plan_linear(&p[3], gemm::EPI_RESID, hid, 4 * D, w.fc2_w, M, D, 4 * D));
+    p[3].args.bias = w.fc2_b;
+    p[3].args.resid = xres;
+    p[3].args.out = xres;
+  }
+  if (m->L > 0) PLAN_TRY(ops::attention_maps(qkv, B, N, m->heads, &fp->tmq, &fp->tmkv));
+  const Buf* in = &l.in0;
+  for (int i = 0; i < 4 && rc == IG_OK; ++i) {
+    const StageW& s = m->st[i];
+    const Buf& tb = l.t[i];
+    PLAN_TRY(plan_conv(&fp->convt[i], gemm::EPI_CONVT, m, ws, *in, s.ct_w, m->dims[i], m->dims[i + 1], B, true));
+    fp->convt[i].args.bias = s.ct_b;
+    fp->convt[i].args.out = ws + tb.off;
+    fp->convt[i].args.out_guard = tb.guard;
+    if (i < 3) {
+      const Buf& ab = l.a[i];
+      PLAN_TRY(plan_conv(&fp->conv[i], gemm::EPI_CONV, m, ws, tb, s.cv_w, m->dims[i + 1], m->dims[i + 1], B, false));
+      fp->conv[i].args.bias = s.scale;
+      fp->conv[i].args.shift = s.shift;
+      fp->conv[i].args.out = ws + ab.off;
+      fp->conv[i].args.out_guard = ab.guard;
+      in = &ab;
+    } else {
+      PLAN_TRY(plan_conv(&fp->fin, gemm::EPI_FINAL, m, ws, tb, s.cv_w, m->dims[4], m->dims[4], B, false));
+      gemm::Args& a = fp->fin.args;
+      a.bias = s.scale;
+      a.shift = s.shift;
+      a.w1 = m->w1;
+      a.b1 = m->b1;
+      a.nc = m->nc;
+    }
+  }
+#undef PLAN_TRY
+  if (rc != IG_OK) {
+    destroy_plan(fp);
+    return rc;
+  }
+  *out = fp;
+  return IG_OK;
+}
+
+int get_plan(ig_model* m, int batch, char* ws, ig_fwd_plan** out) {
+  for (ig_fwd_plan* fp : m->plans)
+    if (fp->batch == batch && fp->ws == ws) {
+      fp->last_use = ++m->use_ctr;
+      *out = fp;
+      return IG_OK;
+    }
+  if (static_cast<int>(m->plans.size()) >= MAX_PLANS) {  // evict the least recently used plan
+    size_t k = 0;
+    for (size_t i = 1; i < m->plans.size(); ++i)
+      if (m->plans[i]->last_use < m->plans[k]->last_use) k = i;
+    // an executable graph may still be in flight on the caller's stream
+    cudaDeviceSynchronize();
+    destroy_plan(m->plans[k]);
+    m->plans.erase(m->plans.begin() + k);
+  }
+  ig_fwd_plan* fp = nullptr;
+  IG_TRY(build_plan(m, batch, ws, &fp));
+  fp->last_use = ++m->use_ctr;
+  m->plans.push_back(fp);
+  *out = fp;
+  return IG_OK;
+}
+
+// Zero borders of the padded-flat head buffers that no kernel of the forward ever writes (the final LayerNorm and
+// the transposed convolutions store interior pixels only): cleared when this (batch, workspace) layout takes the
+// workspace over, not once per forward (5 launches per step before).
+int prepare_rings(ig_model* m, ig_fwd_plan& fp, cudaStream_t st) {
+  if (m->ring_ws == fp.ws && m->ring_batch == fp.batch) return IG_OK;
+  const Layout& l = fp.l;
+  IG_TRY(ops::zero_ring(fp.ws + l.in0.off + static_cast<size_t>(l.in0.guard) * l.in0.C * 2, fp.batch, l.in0.Hp, l.in0.Wp,
+                        l.in0.C, st));
+  for (int i = 0; i < 4; ++i) {
+    const Buf& tb = l.t[i];
+    IG_TRY(ops::zero_ring(fp.ws + tb.off + static_cast<size_t>(tb.guard) * tb.C * 2, fp.batch, tb.Hp, tb.Wp, tb.C, st));
+  }
+  m->ring_ws = fp.ws;
+  m->ring_batch = fp.batch;
+  return IG_OK;
+}
+
+// Enqueue the kernels of one forward on `st`.  *n_kernels = kernels launched; idx_patch / idx_final = position of the
+// two launches that carry caller pointers (for the graph path).
+int enqueue(ig_model* m, ig_fwd_plan& fp, const FwdIO& io, cudaStream_t st, bool taps, int* n_kernels, int* idx_patch,
+            int* idx_final) {
+  const Layout& l = fp.l;
+  char* ws = fp.ws;
+  const int B = fp.batch, D = m->D, T = m->T, g = m->g, N = m->ntok;
+  const int M = B * N;
+  float* xres = reinterpret_cast<float*>(ws + l.x);
+  bf16* xn = reinterpret_cast<bf16*>(ws + l.xn);
+  bf16* att = reinterpret_cast<bf16*>(ws + l.att);
+  const size_t tap_stride = static_cast<size_t>(M) * D;
+  int nk = 0;
+  auto tap_x = [&](int slot) -> int {
+    if (!taps) return IG_OK;
+    IG_CUDA_OK(cudaMemcpyAsync(m->tap_buf + slot * tap_stride, xres, tap_stride * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    return IG_OK;
+  };
+
+  // ---- kernel 2: tubelet patch embedding (im2col-free: rows are written once, in GEMM order)
+  gemm::Plan* pp = &fp.patch;
+  if (io.x_dtype == IG_F32) {
+    IG_TRY(ops::patchify(static_cast<const float*>(io.x), ws + l.patches, B, m->cfg.in_chans, T, m->cfg.img_size, st));
+    ++nk;
+  } else {
+    if (fp.patch_ext_src != io.x) {
+      IG_TRY(ig_make_tmap_bf16(&fp.patch_ext.tmA, io.x, static_cast<uint64_t>(B) * T * g * g, m->K0, m->K0,
+                               fp.patch_ext.args.a_box_rows, gemm::BK));
+      fp.patch_ext_src = io.x;
+    }
+    pp = &fp.patch_ext;
+  }
+  IG_TRY(ops::init_cls(xres, m->cls, m->pos, B, N, D, st));
+  ++nk;
+  *idx_patch = nk;
+  IG_TRY(gemm::launch(*pp, st));
+  ++nk;
+  IG_TRY(tap_x(0));
+
+  // ---- kernel 3: encoder blocks
+  for (int i = 0; i < m->L; ++i) {
+    const LayerW& w = m->layers[i];
+    const gemm::Plan* p = &fp.enc[static_cast<size_t>(4) * i];
+    IG_TRY(ops::layernorm(xres, w.ln1g, w.ln1b, xn, M, D, 0, 0, 0, 0, 0, st));
+    IG_TRY(gemm::launch(p[0], st));
+    IG_TRY(ops::attention_planned(fp.tmq, fp.tmkv, att, B, N, m->heads, st));
+    IG_TRY(gemm::launch(p[1], st));
+    IG_TRY(ops::layernorm(xres, w.ln2g, w.ln2b, xn, M, D, 0, 0, 0, 0, 0, st));
+    IG_TRY(gemm::launch(p[2], st));
+    IG_TRY(gemm::launch(p[3], st));
+    nk += 7;
+    IG_TRY(tap_x(1 + i));
+  }
+
+  // ---- final norm, written straight into the head's padded-flat input (cls dropped)
+  IG_TRY(ops::layernorm(xres, m->norm_g, m->norm_b, ws + l.in0.off, M, D, 1, N, T, g, l.in0.guard, st));
+  ++nk;
+  if (taps) {  // the same rows in token order, cls included (oracle tap "tokens")
+    IG_TRY(ops::layernorm(xres, m->norm_g, m->norm_b, xn, M, D, 0, 0, 0, 0, 0, st));
+    IG_TRY(ops::cvt_f32(xn, m->tap_buf + (1 + m->L) * tap_stride, static_cast<int64_t>(tap_stride), st));
+  }
+  if (io.feats) {
+    IG_TRY(ops::unpad_to_nchw(ws + l.in0.off, io.feats, B, l.in0.Hp, l.in0.Wp, l.in0.C, l.in0.guard, T, st));
+    ++nk;
+  }
+
+  // ---- kernel 4: segmentation head
+  for (int i = 0; i < 4; ++i) {
+    IG_TRY(gemm::launch(fp.convt[i], st));
+    ++nk;
+    if (i < 3) {
+      IG_TRY(gemm::launch(fp.conv[i], st));
+      ++nk;
+    } else {
+      gemm::Args& a = fp.fin.args;
+      a.logits = io.logits;
+      a.argmax = (m->nc > 1) ? io.argmax : nullptr;
+      a.prob1 = io.prob1;
+      *idx_final = nk;
+      IG_TRY(gemm::launch(fp.fin, st));
+      ++nk;
+    }
+  }
+  *n_kernels = nk;
+  return IG_OK;
+}
+
+bool graphs_disabled_by_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IG_NO_GRAPH");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// Capture one forward into a graph.  Any failure of the graph API leaves the model on the eager path for good
+// (graphs_ok = false, message kept for ig_model_graph_status) -- never an error of the forward itself.
+int capture_graph(ig_model* m, ig_fwd_plan& fp, const FwdIO& io, unsigned flags, GraphEntry** out) {
+  *out = nullptr;
+  auto give_up = [&](const char* what, cudaError_t e) {
+    snprintf(m->graph_note, sizeof(m->graph_note), "%s: %s", what, cudaGetErrorString(e));
+    m->graphs_ok = false;
+    cudaGetLastError();
+    return IG_OK;
+  };
+  cudaError_t e;
+  if (!m->cap_stream) {
+    e = cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return give_up("cudaStreamCreateWithFlags", e);
+  }
+  // Nothing executes on cap_stream: it only records the launches (the caller's stream may be the legacy default
+  // stream, which cannot be captured).
+  e = cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) return give_up("cudaStreamBeginCapture", e);
+  int nk = 0, ip = -1, ifin = -1;
+  const int rc = enqueue(m, fp, io, m->cap_stream, false, &nk, &ip, &ifin);
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(m->cap_stream, &graph);
+  if (rc != IG_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;  // a real planning / launch-configuration error: report it
+  }
+  if (e != cudaSuccess || !graph) return give_up("cudaStreamEndCapture", e);
+  // the capture of a single stream is a chain: walk it from the root to number the kernel nodes
+  std::vector<cudaGraphNode_t> chain;
+  {
+    size_t nroot = 0;
+    e = cudaGraphGetRootNodes(graph, nullptr, &nroot);
+    cudaGraphNode_t cur = nullptr;
+    if (e == cudaSuccess && nroot == 1) {
+      size_t one = 1;
+      e = cudaGraphGetRootNodes(graph, &cur, &one);
+    } else if (e == cudaSuccess) {
+      e = cudaErrorUnknown;
+    }
+    while (e == cudaSuccess && cur) {
+      cudaGraphNodeType ty;
+      e = cudaGraphNodeGetType(cur, &ty);
+      if (e != cudaSuccess) break;
+      if (ty != cudaGraphNodeTypeKernel) { e = cudaErrorUnknown; break; }
+      chain.push_back(cur);
+      size_t nd = 0;
+      e = cudaGraphNodeGetDependentNodes(cur, nullptr, &nd);
+      if (e != cudaSuccess) break;
+      if (nd == 0) break;
+      if (nd != 1) { e = cudaErrorUnknown; break; }
+      cudaGraphNode_t nxt = nullptr;
+      size_t one = 1;
+      e = cudaGraphNodeGetDependentNodes(cur, &nxt, &one);
+      cur = nxt;
+    }
+  }
+  if (e != cudaSuccess || static_cast<int>(chain.size()) != nk || ip < 0 || ifin < 0) {
+    cudaGraphDestroy(graph);
+    return give_up("captured graph is not the expected kernel chain", e == cudaSuccess ? cudaErrorUnknown : e);
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    return give_up("cudaGraphInstantiate", e);
+  }
+  GraphEntry ge;
+  ge.flags = flags;
+  ge.graph = graph;
+  ge.exec = exec;
+  ge.n_patch = chain[ip];
+  ge.n_final = chain[ifin];
+  ge.io = io;
+  fp.graphs.push_back(ge);
+  *out = &fp.graphs.back();
+  m->graph_kernels = nk;
+  return IG_OK;
+}
+
+// Re-point the two kernel nodes that carry caller pointers.  func / grid / block / shared memory are read back from
+// the captured node; the argument list (tmA, tmB, Args) is gemm_kernel's.
+int update_graph(ig_model* m, ig_fwd_plan& fp, GraphEntry& ge, const FwdIO& io) {
+  cudaError_t e = cudaSuccess;
+  if (io.x != ge.io.x) {
+    if (fp.patch_ext_src != io.x) {
+      IG_TRY(ig_make_tmap_bf16(&fp.patch_ext.tmA, io.x, static_cast<uint64_t>(fp.batch) * m->T * m->g * m->g, m->K0,
+                               m->K0, fp.patch_ext.args.a_box_rows, gemm::BK));
+      fp.patch_ext_src = io.x;
+    }
+    cudaKernelNodeParams kp;
+    e = cudaGraphKernelNodeGetParams(ge.n_patch, &kp);
+    if (e == cudaSuccess) {
+      void* args[3] = {&fp.patch_ext.tmA, &fp.patch_ext.tmB, &fp.patch_ext.args};
+      kp.kernelParams = args;
+      kp.extra = nullptr;
+      e = cudaGraphExecKernelNodeSetParams(ge.exec, ge.n_patch, &kp);
+    }
+  }
+  if (e == cudaSuccess && (io.logits != ge.io.logits || io.argmax != ge.io.argmax || io.prob1 != ge.io.prob1)) {
+    gemm::Args& a = fp.fin.args;
+    a.logits = io.logits;
+    a.argmax = (m->nc > 1) ? io.argmax : nullptr;
+    a.prob1 = io.prob1;
+    cudaKernelNodeParams kp;
+    e = cudaGraphKernelNodeGetParams(ge.n_final, &kp);
+    if (e == cudaSuccess) {
+      void* args[3] = {&fp.fin.tmA, &fp.fin.tmB, &fp.fin.args};
+      kp.kernelParams = args;
+      kp.extra = nullptr;
+      e = cudaGraphExecKernelNodeSetParams(ge.exec, ge.n_final, &kp);
+    }
+  }
+  if (e != cudaSuccess) {
+    snprintf(m->graph_note, sizeof(m->graph_note), "graph node update: %s", cudaGetErrorString(e));
+    m->graphs_ok = false;
+    cudaGetLastError();
+    return IG_ESTATE;  // caller falls back to the eager path for this call
+  }
+  ge.io = io;
+  return IG_OK;
+}
+
+}  // namespace
+
 static int forward_impl(ig_model* m, const void* x, int x_dtype, int batch, float* logits, int8_t* argmax,
                         float* prob1, float* feats, void* workspace, size_t workspace_bytes, void* stream) {
   IG_TRY(ig_check_device());
@@ -434,103 +866,60 @@ static int forward_impl(ig_model* m, const void* x, int x_dtype, int batch, floa
   IG_REQUIRE(batch >= 1, IG_ESHAPE, "ig_model_forward: batch %d", batch);
   IG_REQUIRE(x_dtype == IG_F32 || x_dtype == IG_BF16, IG_EINVAL, "ig_model_forward: x_dtype must be IG_F32 or IG_BF16");
   IG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, IG_EINVAL, "workspace must be 1024-byte aligned");
-  const Layout l = make_layout(m, batch);
-  IG_REQUIRE(workspace_bytes >= l.total, IG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, l.total);
   IG_REQUIRE(static_cast<int64_t>(batch) * (226 * 226) < (1ll << 31) - 4096, IG_ESHAPE, "batch %d too large", batch);
+  {
+    int dev = -1;
+    IG_CUDA_OK(cudaGetDevice(&dev));
+    IG_REQUIRE(dev == m->device, IG_ESTATE, "ig_model_forward: model lives on device %d, current device is %d", m->device, dev);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
-  const int B = batch, D = m->D, T = m->T, g = m->g, N = m->ntok;
-  const int M = B * N, MP = B * T * g * g;
-  float* xres = reinterpret_cast<float*>(ws + l.x);
-  bf16* xn = reinterpret_cast<bf16*>(ws + l.xn);
-  bf16* qkv = reinterpret_cast<bf16*>(ws + l.qkv);
-  bf16* att = reinterpret_cast<bf16*>(ws + l.att);
-  bf16* hid = reinterpret_cast<bf16*>(ws + l.hid);
-
-  // ---- kernel 2: tubelet patch embedding (im2col-free: rows are written once, in GEMM order)
-  const void* patches = x;
-  if (x_dtype == IG_F32) {
-    IG_TRY(ops::patchify(static_cast<const float*>(x), ws + l.patches, B, m->cfg.in_chans, T, m->cfg.img_size, st));
-    patches = ws + l.patches;
+  ig_fwd_plan* fp = nullptr;
+  IG_TRY(get_plan(m, batch, ws, &fp));
+  IG_REQUIRE(workspace_bytes >= fp->l.total, IG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, fp->l.total);
+  const bool taps = m->tap_buf != nullptr;
+  if (taps) {
+    const size_t need = static_cast<size_t>(m->L + 2) * batch * m->ntok * m->D;
+    IG_REQUIRE(m->tap_elems >= need, IG_ENOMEM, "tap buffer holds %zu floats, batch %d needs %zu", m->tap_elems, batch, need);
+    m->tap_batch = batch;
   }
-  IG_TRY(ops::init_cls(xres, m->cls, m->pos, B, N, D, st));
-  gemm::Plan p;
-  IG_TRY(gemm::plan_linear(&p, gemm::EPI_PATCH, patches, m->K0, m->pe_w, MP, D, m->K0));
-  p.args.bias = m->pe_b;
-  p.args.pos = m->pos;
-  p.args.tok_per_img = T * g * g;
-  p.args.ntok = N;
-  p.args.out = xres;
-  IG_TRY(gemm::launch(p, st));
+  IG_TRY(prepare_rings(m, *fp, st));
+  const FwdIO io{x, x_dtype, logits, argmax, prob1, feats};
+  int nk = 0, ip = -1, ifin = -1;
 
-  // ---- kernel 3: encoder blocks
-  for (int i = 0; i < m->L; ++i) {
-    const LayerW& w = m->layers[i];
-    IG_TRY(ops::layernorm(xres, w.ln1g, w.ln1b, xn, M, D, 0, 0, 0, 0, 0, st));
-    IG_TRY(gemm::plan_linear(&p, gemm::EPI_BF16, xn, D, w.qkv_w, M, 3 * D, D));
-    p.args.bias = w.qkv_b;
-    p.args.out = qkv;
-    IG_TRY(gemm::launch(p, st));
-    IG_TRY(ops::attention(qkv, att, B, N, m->heads, st));
-    IG_TRY(gemm::plan_linear(&p, gemm::EPI_RESID, att, D, w.proj_w, M, D, D));
-    p.args.bias = w.proj_b;
-    p.args.resid = xres;
-    p.args.out = xres;
-    IG_TRY(gemm::launch(p, st));
-    IG_TRY(ops::layernorm(xres, w.ln2g, w.ln2b, xn, M, D, 0, 0, 0, 0, 0, st));
-    IG_TRY(gemm::plan_linear(&p, gemm::EPI_BF16, xn, D, w.fc1_w, M, 4 * D, D));
-    p.args.bias = w.fc1_b;
-    p.args.act = 1;
-    p.args.out = hid;
-    IG_TRY(gemm::launch(p, st));
-    IG_TRY(gemm::plan_linear(&p, gemm::EPI_RESID, hid, 4 * D, w.fc2_w, M, D, 4 * D));
-    p.args.bias = w.fc2_b;
-    p.args.resid = xres;
-    p.args.out = xres;
-    IG_TRY(gemm::launch(p, st));
-  }
-
-  // ---- final norm, written straight into the head's padded-flat input (cls dropped)
-  IG_TRY(ops::zero_ring(ws + l.in0.off + static_cast<size_t>(l.in0.guard) * l.in0.C * 2, B, l.in0.Hp, l.in0.Wp,
-                        l.in0.C, st));
-  IG_TRY(ops::layernorm(xres, m->norm_g, m->norm_b, ws + l.in0.off, M, D, 1, N, T, g, l.in0.guard, st));
-  if (feats)
-    IG_TRY(ops::unpad_to_nchw(ws + l.in0.off, feats, B, l.in0.Hp, l.in0.Wp, l.in0.C, l.in0.guard, T, st));
-
-  // ---- kernel 4: segmentation head
-  const Buf* in = &l.in0;
-  for (int i = 0; i < 4; ++i) {
-    const StageW& s = m->st[i];
-    const Buf& tb = l.t[i];
-    IG_TRY(ops::zero_ring(ws + tb.off + static_cast<size_t>(tb.guard) * tb.C * 2, B, tb.Hp, tb.Wp, tb.C, st));
-    IG_TRY(plan_conv(&p, gemm::EPI_CONVT, m, ws, *in, s.ct_w, m->dims[i], m->dims[i + 1], B, true));
-    p.args.bias = s.ct_b;
-    p.args.out = ws + tb.off;
-    p.args.out_guard = tb.guard;
-    IG_TRY(gemm::launch(p, st));
-    if (i < 3) {
-      const Buf& ab = l.a[i];
-      IG_TRY(plan_conv(&p, gemm::EPI_CONV, m, ws, tb, s.cv_w, m->dims[i + 1], m->dims[i + 1], B, false));
-      p.args.bias = s.scale;
-      p.args.shift = s.shift;
-      p.args.out = ws + ab.off;
-      p.args.out_guard = ab.guard;
-      IG_TRY(gemm::launch(p, st));
-      in = &ab;
-    } else {
-      IG_TRY(plan_conv(&p, gemm::EPI_FINAL, m, ws, tb, s.cv_w, m->dims[4], m->dims[4], B, false));
-      p.args.bias = s.scale;
-      p.args.shift = s.shift;
-      p.args.w1 = m->w1;
-      p.args.b1 = m->b1;
-      p.args.nc = m->nc;
-      p.args.logits = logits;
-      p.args.argmax = (m->nc > 1) ? argmax : nullptr;
-      p.args.prob1 = prob1;
-      IG_TRY(gemm::launch(p, st));
+  bool use_graph = m->graphs_ok && !graphs_disabled_by_env() && !taps && !ig::prof_enabled() &&
+                   x_dtype == IG_BF16 && feats == nullptr;
+  if (use_graph) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      use_graph = false;  // the caller is capturing: our launches become nodes of THEIR graph
     }
   }
-  return IG_OK;
+  if (use_graph) {
+    const unsigned flags = (logits ? 1u : 0u) | (argmax ? 2u : 0u) | (prob1 ? 4u : 0u);
+    GraphEntry* ge = nullptr;
+    for (GraphEntry& g : fp->graphs)
+      if (g.flags == flags) ge = &g;
+    if (!ge) IG_TRY(capture_graph(m, *fp, io, flags, &ge));
+    if (ge) {
+      int rc = IG_OK;
+      if (io.x != ge->io.x || io.logits != ge->io.logits || io.argmax != ge->io.argmax || io.prob1 != ge->io.prob1)
+        rc = update_graph(m, *fp, *ge, io);
+      if (rc == IG_OK) {
+        const cudaError_t e = cudaGraphLaunch(ge->exec, st);
+        if (e == cudaSuccess) {
+          m->last_path = 1;
+          return IG_OK;
+        }
+        snprintf(m->graph_note, sizeof(m->graph_note), "cudaGraphLaunch: %s", cudaGetErrorString(e));
+        m->graphs_ok = false;
+        cudaGetLastError();
+      }
+    }
+  }
+  m->last_path = 0;
+  return enqueue(m, *fp, io, st, taps, &nk, &ip, &ifin);
 }
 
 extern "C" int ig_model_forward(ig_model* m, const void* x, int x_dtype, int batch, float* logits, int8_t* argmax,
@@ -545,6 +934,36 @@ extern "C" int ig_model_predict_proba(ig_model* m, const void* x, int x_dtype, i
   return forward_impl(m, x, x_dtype, batch, nullptr, nullptr, prob_pos, nullptr, workspace, workspace_bytes, stream);
 }
 
+extern "C" int ig_model_reset_cache(ig_model* m) {
+  IG_REQUIRE(m, IG_EINVAL, "ig_model_reset_cache: null model");
+  if (!m->plans.empty()) cudaDeviceSynchronize();
+  for (ig_fwd_plan* fp : m->plans) destroy_plan(fp);
+  m->plans.clear();
+  m->ring_ws = nullptr;
+  m->ring_batch = 0;
+  return IG_OK;
+}
+
+extern "C" int ig_model_set_tap_buffer(ig_model* m, float* buf, size_t elems) {
+  IG_REQUIRE(m, IG_EINVAL, "ig_model_set_tap_buffer: null model");
+  m->tap_buf = buf;
+  m->tap_elems = buf ? elems : 0;
+  m->tap_batch = 0;
+  return IG_OK;
+}
+
+extern "C" int ig_model_graph_status(const ig_model* m, int* last_forward_was_graph, int* kernels_in_graph,
+                                     char* note, size_t note_bytes) {
+  IG_REQUIRE(m, IG_EINVAL, "ig_model_graph_status: null model");
+  if (last_forward_was_graph) *last_forward_was_graph = m->last_path;
+  if (kernels_in_graph) *kernels_in_graph = m->graph_kernels;
+  if (note && note_bytes) {
+    strncpy(note, m->graph_note, note_bytes - 1);
+    note[note_bytes - 1] = 0;
+  }
+  return m->graphs_ok ? 1 : 0;
+}
+
 extern "C" int ig_model_debug_tap(ig_model* m, const char* name, int batch, void* workspace, float* dst,
                                   size_t dst_elems, void* stream) {
   IG_REQUIRE(m && name && workspace && dst, IG_EINVAL, "ig_model_debug_tap: null pointer");
@@ -557,12 +976,30 @@ extern "C" int ig_model_debug_tap(ig_model* m, const char* name, int batch, void
     IG_CUDA_OK(cudaMemcpyAsync(dst, ws + l.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return IG_OK;
   }
+  // encoder taps [B, N, D] recorded by the last forward into the buffer of ig_model_set_tap_buffer
+  int slot = -1;
+  if (!strcmp(name, "embed")) slot = 0;
+  else if (!strcmp(name, "tokens")) slot = 1 + m->L;
+  else if (starts_with(name, "block")) {
+    char* end = nullptr;
+    const long bi = strtol(name + 5, &end, 10);
+    IG_REQUIRE(end && *end == 0 && end != name + 5 && bi >= 0 && bi < m->L, IG_EINVAL, "unknown tap '%s' (block0..block%d)", name, m->L - 1);
+    slot = 1 + static_cast<int>(bi);
+  }
+  if (slot >= 0) {
+    IG_REQUIRE(m->tap_buf != nullptr && m->tap_batch == batch, IG_ESTATE,
+               "tap '%s': call ig_model_set_tap_buffer before the forward (recorded batch %d, asked %d)", name, m->tap_batch, batch);
+    const size_t n = static_cast<size_t>(batch) * m->ntok * m->D;
+    IG_REQUIRE(dst_elems >= n, IG_ENOMEM, "tap %s needs %zu elements", name, n);
+    IG_CUDA_OK(cudaMemcpyAsync(dst, m->tap_buf + slot * n, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return IG_OK;
+  }
   const Buf* b = nullptr;
   int permT = 1;
   if (!strcmp(name, "feat")) { b = &l.in0; permT = m->T; }
   else if (starts_with(name, "convt") && name[5] >= '0' && name[5] <= '3') b = &l.t[name[5] - '0'];
   else if (starts_with(name, "stage") && name[5] >= '0' && name[5] <= '2') b = &l.a[name[5] - '0'];
-  IG_REQUIRE(b != nullptr, IG_EINVAL, "unknown tap '%s' (x, feat, convt0-3, stage0-2)", name);
+  IG_REQUIRE(b != nullptr, IG_EINVAL, "unknown tap '%s' (x, embed, block<i>, tokens, feat, convt0-3, stage0-2)", name);
   const size_t n = static_cast<size_t>(batch) * b->C * (b->Hp - 2) * (b->Wp - 2);
   IG_REQUIRE(dst_elems >= n, IG_ENOMEM, "tap %s needs %zu elements", name, n);
   return ops::unpad_to_nchw(ws + b->off, dst, batch, b->Hp, b->Wp, b->C, b->guard, permT, st);

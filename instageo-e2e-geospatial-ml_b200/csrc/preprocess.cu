@@ -407,6 +407,88 @@ void launch_pre_i16(const PreArgs& a, unsigned blocks, int threads, cudaStream_t
     preprocess_i16x6_kernel<RawT, false><<<blocks, threads, 0, st>>>(a);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tile-level "any selected band is nodata" map for the sliding-window stitch (kernel 5's nodata override):
+// the SAME per-element test as above (cloud pixels replaced by the fill value before scaling, float64
+// product compared with no_data_value, dataloader.py:741, :899), evaluated once per output pixel of a row range
+// of the tile instead of once per window and scattered (one launch instead of a mask-only preprocess launch over
+// the non-overlapping window subset plus up to four strided copies).  Thread = 8 consecutive pixels of a row.
+struct NdArgs {
+  const void* raw;
+  int64_t band_stride, row_stride;
+  const int32_t* band_idx;
+  int T, C, H, W, y0, y1;
+  double cm, nodata;
+  int cm_is_one, fill_raw;
+  const uint8_t* fmask;
+  uint32_t fmask_bits;
+  int mask_any;
+  uint8_t* out;
+};
+
+template <typename RawT>
+__global__ void __launch_bounds__(256) nodata_map_kernel(const NdArgs a) {
+  typedef typename RawVal<RawT>::type ValT;
+  const int gpr = (a.W + VEC - 1) / VEC;
+  const int64_t total = static_cast<int64_t>(a.y1 - a.y0) * gpr;
+  const RawT* raw = static_cast<const RawT*>(a.raw);
+  const int TC = a.T * a.C;
+  for (int64_t item = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; item < total;
+       item += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(item % gpr);
+    const int y = a.y0 + static_cast<int>(item / gpr);
+    const int x = g * VEC;
+    const int nvalid = min(VEC, a.W - x);
+    uint32_t cloud_t[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) cloud_t[i] = 0;
+    if (a.fmask) {
+      for (int t = 0; t < a.T; ++t) {
+        const uint8_t* fm = a.fmask + (static_cast<int64_t>(t) * a.H + y) * static_cast<int64_t>(a.W) + x;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (i < nvalid && fmask_hit(__ldg(fm + i), a.fmask_bits)) cloud_t[i] |= (1u << t);
+      }
+      if (a.mask_any) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) cloud_t[i] = cloud_t[i] ? 0xffffffffu : 0u;
+      }
+    }
+    uint32_t m = 0;
+    for (int tc = 0; tc < TC; ++tc) {
+      const int t = tc / a.C;
+      const RawT* src = raw + __ldg(a.band_idx + tc) * a.band_stride + static_cast<int64_t>(y) * a.row_stride + x;
+      ValT v[VEC];
+      if (nvalid == VEC) {
+        load8<RawT>(src, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = i < nvalid ? static_cast<ValT>(__ldg(src + i)) : ValT(0);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        ValT rv = v[i];
+        if (cloud_t[i] & (1u << t)) rv = a.fill_raw;
+        const bool nd = a.cm_is_one ? (static_cast<double>(rv) == a.nodata)
+                                    : (__dmul_rn(static_cast<double>(rv), a.cm) == a.nodata);
+        if (nd) m |= (1u << i);
+      }
+    }
+    uint8_t* dst = a.out + static_cast<int64_t>(y - a.y0) * a.W + x;
+    if (nvalid == VEC && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+      uint2 q;
+      q.x = ((m >> 0) & 1u) | (((m >> 1) & 1u) << 8) | (((m >> 2) & 1u) << 16) | (((m >> 3) & 1u) << 24);
+      q.y = ((m >> 4) & 1u) | (((m >> 5) & 1u) << 8) | (((m >> 6) & 1u) << 16) | (((m >> 7) & 1u) << 24);
+      *reinterpret_cast<uint2*>(dst) = q;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        if (i < nvalid) dst[i] = static_cast<uint8_t>((m >> i) & 1u);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_src_bands, int H,
@@ -490,6 +572,55 @@ extern "C" int ig_preprocess(const void* raw, int raw_dtype, int n_img, int n_sr
     launch_pre<float>(a, static_cast<unsigned>(blocks), threads, st);
   else
     launch_pre<double>(a, static_cast<unsigned>(blocks), threads, st);
+  IG_CUDA_OK(cudaGetLastError());
+  return IG_OK;
+}
+
+extern "C" int ig_nodata_map(const void* raw, int raw_dtype, int n_src_bands, int H, int W, int64_t band_stride,
+                             int64_t row_stride, const int32_t* band_idx, int T, int C, double constant_multiplier,
+                             int has_nodata, double no_data_value, const uint8_t* fmask, uint32_t fmask_bits,
+                             int masking_strategy, int y0, int y1, uint8_t* out, void* stream) {
+  IG_TRY(ig_check_device());
+  IG_REQUIRE(raw && band_idx && out, IG_EINVAL, "ig_nodata_map: null pointer");
+  IG_REQUIRE(raw_dtype == IG_I16 || raw_dtype == IG_U16 || raw_dtype == IG_F32 || raw_dtype == IG_F64, IG_EINVAL,
+             "ig_nodata_map: raw_dtype must be IG_I16, IG_U16, IG_F32 or IG_F64");
+  IG_REQUIRE(T >= 1 && C >= 1 && T * C <= MAX_TC && T <= 32 && n_src_bands >= 1, IG_ESHAPE, "ig_nodata_map: unsupported T=%d C=%d", T, C);
+  IG_REQUIRE(H >= 1 && W >= 1 && y0 >= 0 && y0 <= y1 && y1 <= H, IG_ESHAPE, "ig_nodata_map: rows [%d, %d) of %d x %d", y0, y1, H, W);
+  IG_REQUIRE(masking_strategy == IG_MASK_EACH || masking_strategy == IG_MASK_ANY, IG_EINVAL, "ig_nodata_map: bad masking strategy");
+  if (y1 == y0) return IG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool use_fmask = fmask != nullptr && fmask_bits != 0;
+  if (!has_nodata && !use_fmask) {  // nothing can be flagged
+    IG_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(y1 - y0) * W, st));
+    return IG_OK;
+  }
+  NdArgs a;
+  a.raw = raw;
+  a.band_stride = band_stride;
+  a.row_stride = row_stride;
+  a.band_idx = band_idx;
+  a.T = T, a.C = C, a.H = H, a.W = W, a.y0 = y0, a.y1 = y1;
+  a.cm = constant_multiplier;
+  // without a nodata value the element test of ig_preprocess is never true, whatever the cloud fill: an
+  // unreachable comparand (NaN) states exactly that
+  a.nodata = has_nodata ? no_data_value : __builtin_nan("");
+  a.cm_is_one = constant_multiplier == 1.0;
+  a.fill_raw = has_nodata ? static_cast<int>(no_data_value) : 0;
+  a.fmask = use_fmask ? fmask : nullptr;
+  a.fmask_bits = fmask_bits;
+  a.mask_any = masking_strategy == IG_MASK_ANY;
+  a.out = out;
+  const int64_t total = static_cast<int64_t>(y1 - y0) * ((W + VEC - 1) / VEC);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(ig_num_sms()) * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  ig::ProfScope prof(ig::PROF_PREPROCESS, st);
+  switch (raw_dtype) {
+    case IG_I16: nodata_map_kernel<int16_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a); break;
+    case IG_U16: nodata_map_kernel<uint16_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a); break;
+    case IG_F32: nodata_map_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a); break;
+    default: nodata_map_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a); break;
+  }
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }

@@ -175,7 +175,7 @@ __device__ __forceinline__ void rows_vec(const StitchArgs& a, const int* ysrc, c
 #pragma unroll
     for (int q = 0; q < PX; ++q) c4[q] = cnt > 0 ? bi[r][q] : a.nodata_class;
     if (a.nodata_px) {
-      const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(a.nodata_px + static_cast<int64_t>(y + r) * a.W + x0));
+      const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(a.nodata_px + static_cast<int64_t>(y + r - a.y0) * a.W + x0));
 #pragma unroll
       for (int q = 0; q < PX; ++q)
         if ((m >> (8 * q)) & 0xffu) c4[q] = a.nodata_class;
@@ -231,7 +231,7 @@ __device__ __noinline__ void row_scalar(const StitchArgs& a, const int* ysrc, co
         }
     }
     int c = cnt > 0 ? bi : a.nodata_class;
-    if (a.nodata_px && a.nodata_px[static_cast<int64_t>(y) * a.W + x]) c = a.nodata_class;
+    if (a.nodata_px && a.nodata_px[static_cast<int64_t>(y - a.y0) * a.W + x]) c = a.nodata_class;
     a.cls[static_cast<int64_t>(y - a.y0) * a.W + x] = static_cast<int8_t>(c);
   }
 }
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(T_THREADS) stitch_tma_kernel(const __grid_cons
     const int y = tile_y0 + r0 + j;
     ndw[j] = 0;
     if (a.nodata_px && y < tile_y1 && x0 < a.W) {
-      const uint8_t* nd = a.nodata_px + static_cast<int64_t>(y) * a.W + x0;
+      const uint8_t* nd = a.nodata_px + static_cast<int64_t>(y - a.y0) * a.W + x0;
       if (ta.vst) ndw[j] = __ldg(reinterpret_cast<const uint32_t*>(nd));
       else
         for (int q = 0; q < PX; ++q)
@@ -552,10 +552,10 @@ int launch_tma(const CUtensorMap& tm, TileArgs ta, cudaStream_t st) {
   constexpr int TR = 4 * RT;
   const size_t stage = static_cast<size_t>(CH) * TR * PITCH * 4;
   const size_t smem = 128 + stage * ta.stages;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static IgPerDevice configured = {};
+  if (static_cast<int>(smem) > configured.get()) {
     IG_CUDA_OK(cudaFuncSetAttribute(stitch_tma_kernel<CH, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+    configured.set(static_cast<int>(smem));
   }
   ta.nseg = (ta.s.W + SEG - 1) / SEG;
   const long long ntiles = static_cast<long long>(ta.nseg) * ((ta.s.y1 - ta.s.y0 + TR - 1) / TR);

@@ -74,16 +74,25 @@ def create_chip(chip, fmask=None, seg_map=None, masking_strategy: str = "each",
         steps, bits = fm.shape[0], _bits(data_source, mask_types)
     seg_in = seg_out = None
     if seg_map is not None:
-        seg_in = _dev(seg_map, x.device).reshape(H, W).to(torch.int8).contiguous()
+        seg_in = _dev(seg_map, x.device).reshape(H, W)
+        # The reference keeps the label map's dtype (float32 for regression targets, hls_utils.py:398); the device
+        # kernel carries int8 class labels only.  Refuse anything a cast to int8 would change instead of truncating.
+        if seg_in.is_floating_point() or seg_in.dtype == torch.bool:
+            raise TypeError("create_chip: seg_map must hold integer class labels (float regression targets are not "
+                            "supported by the device path; mask them with the reference's xarray chain)")
+        if seg_in.dtype != torch.int8:
+            if seg_in.numel() and (int(seg_in.max()) > 127 or int(seg_in.min()) < -128):
+                raise ValueError("create_chip: seg_map labels must fit int8 ([-128, 127])")
+            seg_in = seg_in.to(torch.int8)
+        seg_in = seg_in.contiguous()
         seg_out = torch.empty_like(seg_in)
     out = torch.empty((nb, H, W), dtype=torch.uint16 if clip is not None else x.dtype, device=x.device)
     counts = torch.zeros(2, dtype=torch.int64, device=x.device)
     lo, hi = (int(clip[0]), int(clip[1])) if clip is not None else (1, 0)
     st = _strategy(masking_strategy)
-    _lib.check(_lib.load().ig_chip_mask(
-        x.data_ptr(), _CHIP_DTYPES[x.dtype], nb, H, W, _lib.ptr(fm), steps, bits, st, int(no_data_value), lo, hi,
-        out.data_ptr(), _lib.ptr(seg_in), st, int(seg_no_data_value), _lib.ptr(seg_out), counts.data_ptr(),
-        _lib.current_stream()))
+    _lib.call("ig_chip_mask", x.device,
+              x.data_ptr(), _CHIP_DTYPES[x.dtype], nb, H, W, _lib.ptr(fm), steps, bits, st, int(no_data_value), lo, hi,
+              out.data_ptr(), _lib.ptr(seg_in), st, int(seg_no_data_value), _lib.ptr(seg_out), counts.data_ptr())
     return out, seg_out, counts
 
 

@@ -134,95 +134,11 @@ def gather_chip_masks(local: torch.Tensor, n_total: int, world_size: int) -> tor
 
 
 # --------------------------------------------------------------------------- sliding window
-@torch.no_grad()
-def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224), stride: int = 224,
-                             batch_size: int = 32, device: str = "gpu", *, mean: Sequence[float],
-                             std: Sequence[float], bands: Optional[Sequence[int]] = None,
-                             constant_multiplier: float = 1.0, no_data_value: Optional[float] = None,
-                             nodata_class: int = -1, rows: Optional[tuple[int, int]] = None,
-                             return_tensor: bool = False, fmask=None, fmask_bits: int = 0,
-                             masking_strategy: str = "each", exchange: Optional[tuple[int, int]] = None):
-    """Overlap-averaged class map of a raw tile [T*C (or more bands), H, W] (int16 | uint16).
-
-    windows -> fused normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4) -> gather-form
-    overlap average + argmax + nodata (kernel 5).  ``rows=(y0, y1)`` restricts the output to a
-    row stripe and only the windows touching it are computed (multi-GPU halo recompute);
-    per-pixel sums are formed on one rank in fixed order, so any sharding is bit-identical.
-    ``exchange=(rank, world_size)`` (with ``rows``): the rank computes only ITS share of the window rows
-    (``partition(len(ys), world_size, rank)``) and the window rows its stripe needs from other ranks arrive
-    over NCCL send/recv (``exchange_window_rows``) -- no recomputed halo windows, same bits.
-    Returns int8 [y1-y0, W] (numpy unless ``return_tensor``).
-    """
-    device = "cuda" if device == "gpu" else device
-    win = int(window_size[0])
-    if window_size[0] != window_size[1] or win != model.image_size:
-        raise ValueError("window must be square and match the model's image_size")
-    from .dataloader import _to_device
-
-    tile = _to_device(hls_tile, device)
-    if tile.dim() != 3:
-        raise ValueError("hls_tile must be [bands, H, W]")
-    _, H, W = tile.shape
-    if H < win or W < win:
-        raise ValueError(f"tile {H}x{W} is smaller than the window {win}")
-    model.eval()
-    model.to(device)
-    spec = ops.PreprocessSpec(mean, std, model.temporal_step, bands, constant_multiplier, no_data_value, device)
-    ys = ops.window_origins(H, win, stride, edge=True)
-    xs = ops.window_origins(W, win, stride, edge=True)
-    y0, y1 = rows if rows is not None else (0, H)
-    iy_lo, iy_hi = windows_for_rows(ys, win, y0, y1)
-    nx = len(xs)
-    own_lo, own_hi = (iy_lo, iy_hi) if exchange is None else partition(len(ys), exchange[1], exchange[0])
-    wins = [(0, ys[iy], xs[ix]) for iy in range(own_lo, own_hi) for ix in range(nx)]
-    n_win = len(wins)
-    nc = model.num_classes
-    win_t = torch.tensor(wins, dtype=torch.int32, device=device).reshape(-1, 3)
-    logits = torch.empty((n_win, nc, win, win), dtype=torch.float32, device=device)
-    fm = None if fmask is None else _to_device(fmask, device).unsqueeze(0)
-    # equal-sized model calls of at most batch_size windows (289 windows, batch 256 -> 145 + 144, not 256 + 33:
-    # a small tail call runs the persistent GEMMs at a fraction of a wave)
-    n_calls = max(1, -(-n_win // batch_size))
-    per_call = max(1, -(-n_win // n_calls))
-    for s in range(0, n_win, per_call):
-        e = min(n_win, s + per_call)
-        pre = ops.preprocess(tile.unsqueeze(0), spec, windows=win_t[s:e], win=win, want_f32=False,
-                             want_patches=True, fmask=fm, fmask_bits=fmask_bits,
-                             masking_strategy=masking_strategy)
-        logits[s:e] = model.forward_patches(pre["patches"], want_logits=True)[0]
-    if exchange is not None:
-        logits = exchange_window_rows(logits, ys, win, H, nx, exchange[0], exchange[1])
-    nodata_px = None
-    if no_data_value is not None or fm is not None:
-        # tile-level "any band is nodata" mask from the same kernel (one whole-tile window per 16-aligned block
-        # is not needed: mask_px of the windows already covers every output pixel; stitch it with OR)
-        nodata_px = _tile_nodata(tile, spec, H, W, win, ys, xs, fm, fmask_bits, masking_strategy)
-    out = ops.stitch(logits, ys, xs, H, W, y0=y0, y1=y1, win_base=iy_lo * nx, nodata_px=nodata_px,
-                     nodata_class=nodata_class)["class_map"]
-    return out if return_tensor else out.cpu().numpy()
-
-
-def _tile_nodata(tile, spec, H, W, win, ys, xs, fm, fmask_bits, masking_strategy) -> torch.Tensor:
-    """[H, W] bool: pixel is nodata in ANY selected band/timestep (after scaling, dataloader.py:899).
-
-    Uses the non-overlapping subset of windows (stride == win plus the edge-aligned ones) so each
-    pixel's mask is computed by kernel 1 and scattered once.
-    """
-    dev = tile.device
-    ty = ops.window_origins(H, win, win, edge=True)
-    tx = ops.window_origins(W, win, win, edge=True)
-    wl = [(0, t, l) for t in ty for l in tx]
-    wt = torch.tensor(wl, dtype=torch.int32, device=dev)
-    m = ops.preprocess(tile.unsqueeze(0), spec, windows=wt, win=win, want_f32=False, want_mask_px=True,
-                       fmask=fm, fmask_bits=fmask_bits, masking_strategy=masking_strategy)["mask_px"]
-    return scatter_window_masks(m, len(ty), len(tx), H, W, win)
-
-
 def scatter_window_masks(m: torch.Tensor, ny: int, nx: int, H: int, W: int, win: int) -> torch.Tensor:
     """[ny*nx, win, win] masks of the row-major window grid ``window_origins(H, win, win, edge=True)`` x
-    ``window_origins(W, ...)`` -> [H, W], in at most four strided copies (one slice-OR per window was 289
-    tiny launches per 3660^2 tile: milliseconds of host time in a 15 ms step).  The edge-aligned last row /
-    column of windows overlaps its neighbour; the mask is a function of the pixel alone, so overwriting equals OR."""
+    ``window_origins(W, ...)`` -> [H, W], in at most four strided copies.  The edge-aligned last row / column of
+    windows overlaps its neighbour; the mask is a function of the pixel alone, so overwriting equals OR.
+    (The tile engine now computes the map directly with ``ops.nodata_map``; kept as a cross-check.)"""
     M = m.reshape(ny, nx, win, win)
     ry, rx = H // win, W // win                     # regular (non edge-aligned) window rows / columns
     full = torch.empty((H, W), dtype=m.dtype, device=m.device)
@@ -236,30 +152,56 @@ def scatter_window_masks(m: torch.Tensor, ny: int, nx: int, H: int, W: int, win:
     return full
 
 
-def exchange_plan(ys: Sequence[int], win: int, height: int, world_size: int) -> list:
-    """Who sends which window rows to whom.  For every rank: ``(need, own, local, sends, recvs)`` with
-    ``need`` = window rows [lo, hi) covering its output stripe, ``own`` = window rows it computes, ``local`` = their
-    intersection (or None), ``sends[q]`` / ``recvs[q]`` = the row range sent to / received from rank q.  Pure function
-    of the geometry, identical on every rank, so the send/recv lists match pairwise without any handshake."""
-    ny = len(ys)
-    need = [windows_for_rows(ys, win, *stripe_rows(height, world_size, q)) for q in range(world_size)]
-    own = [partition(ny, world_size, q) for q in range(world_size)]
+def interval_plan(need: Sequence[tuple], own: Sequence[tuple]) -> list:
+    """Who sends which units to whom, for ranks that each NEED the contiguous unit range ``need[r]`` and each
+    COMPUTE the contiguous range ``own[r]`` (the ``own`` ranges partition all units).  Per rank:
+    ``(local, sends, recvs)`` with ``local`` = need ∩ own (or None), ``sends[q]`` / ``recvs[q]`` = the unit range sent
+    to / received from rank q.  A pure function of the geometry, identical on every rank, so the send / receive lists
+    match pairwise without a handshake."""
+    world = len(need)
     plan = []
-    for r in range(world_size):
+    for r in range(world):
         lo, hi = max(need[r][0], own[r][0]), min(need[r][1], own[r][1])
         local = (lo, hi) if lo < hi else None
         sends, recvs = {}, {}
-        for q in range(world_size):
+        for q in range(world):
             if q == r:
                 continue
-            lo, hi = max(need[q][0], own[r][0]), min(need[q][1], own[r][1])    # rows q lacks and r owns
+            lo, hi = max(need[q][0], own[r][0]), min(need[q][1], own[r][1])    # units q lacks and r owns
             if lo < hi:
                 sends[q] = (lo, hi)
-            lo, hi = max(need[r][0], own[q][0]), min(need[r][1], own[q][1])    # rows r lacks and q owns
+            lo, hi = max(need[r][0], own[q][0]), min(need[r][1], own[q][1])    # units r lacks and q owns
             if lo < hi:
                 recvs[q] = (lo, hi)
-        plan.append((need[r], own[r], local, sends, recvs))
+        plan.append((local, sends, recvs))
     return plan
+
+
+def exchange_plan(ys: Sequence[int], win: int, height: int, world_size: int) -> list:
+    """Window-ROW form of ``interval_plan``: for every rank ``(need, own, local, sends, recvs)`` with ``need`` =
+    window rows [lo, hi) covering its output stripe ``stripe_rows``, ``own`` = ``partition(len(ys))``."""
+    ny = len(ys)
+    need = [windows_for_rows(ys, win, *stripe_rows(height, world_size, q)) for q in range(world_size)]
+    own = [partition(ny, world_size, q) for q in range(world_size)]
+    return [(need[r], own[r]) + p for r, p in enumerate(interval_plan(need, own))]
+
+
+def _exchange(src: torch.Tensor, src_base: int, dst: torch.Tensor, dst_base: int, sends: dict, recvs: dict,
+              world_size: int) -> list:
+    """Post the point-to-point transfers of one rank's plan entry (unit = first dimension of ``src`` / ``dst``, which
+    hold units ``src_base...`` / ``dst_base...``); returns the outstanding requests.  Per peer: send first, then
+    receive -- the same order on both sides of a pair."""
+    import torch.distributed as dist
+
+    p2p = []
+    for q in range(world_size):
+        if q in sends:
+            lo, hi = sends[q]
+            p2p.append(dist.P2POp(dist.isend, src[lo - src_base:hi - src_base], q))
+        if q in recvs:
+            lo, hi = recvs[q]
+            p2p.append(dist.P2POp(dist.irecv, dst[lo - dst_base:hi - dst_base], q))
+    return dist.batch_isend_irecv(p2p) if p2p else []
 
 
 def exchange_window_rows(own_logits: torch.Tensor, ys: Sequence[int], win: int, height: int, nx: int,
@@ -271,75 +213,344 @@ def exchange_window_rows(own_logits: torch.Tensor, ys: Sequence[int], win: int, 
     ``windows_for_rows(...)``: the rows it lacks are received from their owners, the rows others lack are sent
     (``batch_isend_irecv``: NCCL over NVLink on GPUs, gloo in the CPU tests).  What travels are the window
     LOGITS, not partial sums, so every pixel is still summed on one rank in window order: bit-identical to one GPU,
-    and nobody computes a window twice (halo recompute costs 6 instead of 4 window rows per rank at stride 112
-    on 8 GPUs).  Returns the logits of the needed rows, [(iy_hi - iy_lo) * nx, nc, win, win]."""
-    import torch.distributed as dist
-
+    and nobody computes a window twice.  Returns the logits of the needed rows, [(iy_hi - iy_lo) * nx, ...]."""
     (iy_lo, iy_hi), (own_lo, own_hi), local, sends, recvs = exchange_plan(ys, win, height, world_size)[rank]
     out = torch.empty(((iy_hi - iy_lo) * nx,) + tuple(own_logits.shape[1:]), dtype=own_logits.dtype,
                       device=own_logits.device)
     if local is not None:
         lo, hi = local
         out[(lo - iy_lo) * nx:(hi - iy_lo) * nx] = own_logits[(lo - own_lo) * nx:(hi - own_lo) * nx]
-    p2p = []
-    for q in range(world_size):  # per peer: send first, then receive -- the same order on both sides of a pair
-        if q in sends:
-            lo, hi = sends[q]
-            p2p.append(dist.P2POp(dist.isend, own_logits[(lo - own_lo) * nx:(hi - own_lo) * nx], q))
-        if q in recvs:
-            lo, hi = recvs[q]
-            p2p.append(dist.P2POp(dist.irecv, out[(lo - iy_lo) * nx:(hi - iy_lo) * nx], q))
-    if p2p:
-        for req in dist.batch_isend_irecv(p2p):
-            req.wait()
+    scale = lambda d: {q: (lo * nx, hi * nx) for q, (lo, hi) in d.items()}
+    for req in _exchange(own_logits, own_lo * nx, out, iy_lo * nx, scale(sends), scale(recvs), world_size):
+        req.wait()
     return out
+
+
+def even_stripes(height: int, world_size: int) -> list:
+    """Output row stripes of equal height ``ceil(H / world)`` (the last may be short or empty): every rank's stripe
+    is one slot of a ``[world * rows, W]`` buffer, so the stripes are all-gathered IN PLACE, straight into the map."""
+    rows = -(-height // world_size)
+    return [(min(height, r * rows), min(height, (r + 1) * rows)) for r in range(world_size)]
+
+
+class TileEngine:
+    """Sliding-window inference over rasters of ONE geometry, everything geometry-dependent kept on the device.
+
+    windows -> fused normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4, CUDA-graph replay) -> window-logit
+    exchange (N > 1) -> nodata map -> gather-form overlap average + argmax + nodata (kernel 5) -> stripe all-gather.
+
+    Built once per (model, raster shape, window, stride, preprocessing constants, sharding): the window lists, the
+    band / mean / std tensors, the stitch origin tables, the exchange plan and every buffer (window logits, tubelet
+    rows, nodata map, the gathered class map) live on the device across tiles.  Per tile the host only enqueues
+    work; nothing is built from Python lists and no host-device synchronisation happens (the per-call
+    ``torch.tensor(..., device=)`` copies of the first version stalled the host ~7 times per tile).
+
+    Sharding (``world`` ranks, one process per GPU): rank r stitches output rows ``stripes[r]`` -- which need the
+    whole window rows that touch them -- and COMPUTES the contiguous share ``partition(n_windows, world, r)`` of the
+    row-major window list (balanced to one window; whole window rows per rank left 3-vs-2 rows at stride 224 on 8
+    GPUs).  Windows a rank needs but does not own arrive as LOGITS over NCCL send/recv, so every pixel is still
+    summed on one rank in window order: bit-identical to one GPU.  ``halo_recompute``: every rank instead computes
+    all windows its stripe needs (no exchange).
+    """
+
+    def __init__(self, model: PrithviSeg, shape, raw_dtype, window: int, stride: int, batch_size: int, *,
+                 mean, std, bands=None, constant_multiplier: float = 1.0, no_data_value=None,
+                 nodata_class: int = -1, rank: int = 0, world: int = 1, stripes=None,
+                 halo_recompute: bool = False, fmask_bits: int = 0, masking_strategy: str = "each", device="cuda"):
+        nb, H, W = (int(v) for v in shape)
+        self.model, self.nb, self.H, self.W, self.win, self.stride = model, nb, H, W, int(window), int(stride)
+        if self.win != model.image_size:
+            raise ValueError("window must match the model's image_size")
+        if H < self.win or W < self.win:
+            raise ValueError(f"tile {H}x{W} is smaller than the window {self.win}")
+        self.device = torch.device("cuda" if device == "gpu" else device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.raw_dtype = raw_dtype
+        self.rank, self.world = int(rank), int(world)
+        self.batch_size = max(1, int(batch_size))
+        self.nodata_class = int(nodata_class)
+        self.fmask_bits, self.masking_strategy = int(fmask_bits), masking_strategy
+        model.eval()
+        model.to(self.device)
+        dev = self.device
+        self.spec = ops.PreprocessSpec(mean, std, model.temporal_step, bands, constant_multiplier, no_data_value, dev)
+        self.has_nodata = no_data_value is not None
+        self.ys = ops.window_origins(H, self.win, self.stride, edge=True)
+        self.xs = ops.window_origins(W, self.win, self.stride, edge=True)
+        self.nx, self.n_win = len(self.xs), len(self.ys) * len(self.xs)
+        self.stripes = list(stripes) if stripes is not None else even_stripes(H, self.world)
+        if len(self.stripes) != self.world:
+            raise ValueError("one output stripe per rank")
+        need_rows = [windows_for_rows(self.ys, self.win, a, b) if b > a else (0, 0) for a, b in self.stripes]
+        need = [(lo * self.nx, hi * self.nx) for lo, hi in need_rows]
+        own = need if (halo_recompute or self.world == 1) else [partition(self.n_win, self.world, q)
+                                                                 for q in range(self.world)]
+        self.need, self.own = need[self.rank], own[self.rank]
+        if halo_recompute or self.world == 1:
+            self.sends, self.recvs = {}, {}
+        else:
+            _, self.sends, self.recvs = interval_plan(need, own)[self.rank]
+        self.y0, self.y1 = self.stripes[self.rank]
+        # one logit buffer for the union of what the rank computes and what it stitches: own windows are written
+        # in place by the model, received ones by NCCL, the stitch reads the `need` slice -- no local copies
+        n0, n1 = self.need
+        o0, o1 = self.own
+        spans = [(a, b) for a, b in (self.need, self.own) if b > a]
+        self.u0 = min((a for a, _ in spans), default=0)
+        self.u1 = max((b for _, b in spans), default=0)
+        nc, S = model.num_classes, self.win
+        self.logits = torch.empty((max(1, self.u1 - self.u0), nc, S, S), dtype=torch.float32, device=dev)
+        wl = [(0, self.ys[i // self.nx], self.xs[i % self.nx]) for i in range(o0, o1)]
+        self._wins_abs = torch.tensor(wl, dtype=torch.int32, device=dev).reshape(-1, 3)
+        # host rasters: only the rows this rank touches are uploaded
+        row_spans = [(w[1], w[1] + self.win) for w in wl] + ([(self.y0, self.y1)] if self.y1 > self.y0 else [])
+        r0 = min((a for a, _ in row_spans), default=0)
+        self.r0, self.r1 = r0, max((b for _, b in row_spans), default=r0)
+        self._wins_rel = self._wins_abs.clone()
+        if len(wl):
+            self._wins_rel[:, 1] -= r0
+        self._d_tile = None     # [nb, r1 - r0, W] upload buffer (host input only)
+        self._d_fmask = None
+        n_own = o1 - o0
+        self.n_calls = max(1, -(-n_own // self.batch_size)) if n_own else 0
+        self.per_call = max(1, -(-n_own // self.n_calls)) if n_own else 0
+        rows_pp = model.temporal_step * (S // 16) ** 2
+        self.patches = torch.empty((max(1, self.per_call) * rows_pp, 6 * 256), dtype=torch.bfloat16, device=dev)
+        self.origins = (torch.tensor(self.ys, dtype=torch.int32, device=dev),
+                        torch.tensor(self.xs, dtype=torch.int32, device=dev))
+        self.rows_max = max(1, max(b - a for a, b in self.stripes))
+        self._even = self.stripes == even_stripes(H, self.world)
+        if self._even:
+            self.full = torch.empty((self.world * self.rows_max, W), dtype=torch.int8, device=dev)
+            self.out = self.full[self.rank * self.rows_max:self.rank * self.rows_max + (self.y1 - self.y0)]
+        else:
+            self.full = None
+            self.out = torch.empty((self.y1 - self.y0, W), dtype=torch.int8, device=dev)
+        self.nd = torch.empty((max(1, self.y1 - self.y0), W), dtype=torch.uint8, device=dev)[:self.y1 - self.y0]
+        torch.cuda.current_stream(dev).synchronize()   # the small host->device copies above: once per geometry
+
+    # -- input staging -------------------------------------------------------------------------------------------
+    def _stage(self, tile, fmask):
+        """-> (raster on the device, first raster row it holds, fmask on the device or None)."""
+        if isinstance(tile, np.ndarray):
+            tile = torch.from_numpy(np.ascontiguousarray(tile).view(np.int16) if tile.dtype == np.uint16 else
+                                    np.ascontiguousarray(tile))
+            if self.raw_dtype == torch.uint16:
+                tile = tile.view(torch.uint16)
+        if tile.dim() != 3 or tuple(tile.shape) != (self.nb, self.H, self.W):
+            raise ValueError(f"hls_tile must be [bands, H, W] = {(self.nb, self.H, self.W)}, got {tuple(tile.shape)}")
+        fm = None
+        if tile.is_cuda:
+            if fmask is not None:
+                fm = fmask if isinstance(fmask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fmask))
+                fm = fm.to(self.device)
+            return tile, 0, fm
+        rows = self.r1 - self.r0
+        if self._d_tile is None:
+            self._d_tile = torch.empty((self.nb, max(1, rows), self.W), dtype=tile.dtype, device=self.device)
+        if rows:
+            src = tile[:, self.r0:self.r1]
+            if src.is_contiguous() or not tile.is_pinned():
+                self._d_tile[:, :rows].copy_(src, non_blocking=True)
+            else:   # pinned, strided over bands: one contiguous DMA per band (a strided copy would stage on the host)
+                for b in range(self.nb):
+                    self._d_tile[b, :rows].copy_(src[b], non_blocking=True)
+        if fmask is not None:
+            fm = fmask if isinstance(fmask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fmask))
+            fm = fm[:, self.r0:self.r1].to(self.device, non_blocking=True)
+        return self._d_tile[:, :max(1, rows)], self.r0, fm
+
+    # -- one tile ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, hls_tile, fmask=None, gather: bool = True) -> torch.Tensor:
+        """int8 class map: the whole [H, W] map when ``gather`` (all ranks end up with it), else this rank's stripe
+        [y1-y0, W].  The returned tensor is a VIEW of the engine's buffer: valid until the next ``run``."""
+        with torch.cuda.device(self.device):
+            d_tile, row_off, fm = self._stage(hls_tile, fmask)
+            wins = self._wins_rel if row_off else self._wins_abs
+            raw4 = d_tile.unsqueeze(0)
+            fm4 = None if fm is None else fm.unsqueeze(0)
+            o0, o1 = self.own
+            base = o0 - self.u0
+            for c in range(self.n_calls):
+                s, e = c * self.per_call, min(o1 - o0, (c + 1) * self.per_call)
+                if e <= s:
+                    break
+                pre = ops.preprocess(raw4, self.spec, windows=wins[s:e], win=self.win, want_f32=False,
+                                     want_patches=True, fmask=fm4, fmask_bits=self.fmask_bits,
+                                     masking_strategy=self.masking_strategy, out_patches=self.patches)
+                self.model.forward_patches(pre["patches"], want_logits=True, out_logits=self.logits[base + s:base + e])
+            reqs = _exchange(self.logits, self.u0, self.logits, self.u0, self.sends, self.recvs, self.world) \
+                if (self.sends or self.recvs) else []
+            rows = self.y1 - self.y0
+            nd = None
+            if rows and (self.has_nodata or (fm is not None and self.fmask_bits)):
+                nd = ops.nodata_map(d_tile, self.spec, self.y0 - row_off, self.y1 - row_off, fmask=fm,
+                                    fmask_bits=self.fmask_bits, masking_strategy=self.masking_strategy, out=self.nd)
+            for req in reqs:
+                req.wait()
+            if rows:
+                n0, n1 = self.need
+                ops.stitch(self.logits[n0 - self.u0:n1 - self.u0], self.ys, self.xs, self.H, self.W, y0=self.y0,
+                           y1=self.y1, win_base=n0, nodata_px=nd, nodata_class=self.nodata_class,
+                           origins=self.origins, out=self.out)
+            if not gather or self.world == 1:
+                return self.out
+            return self._gather()
+
+    def _gather(self) -> torch.Tensor:
+        import torch.distributed as dist
+
+        if self._even and dist.get_backend() == "nccl":
+            # in place: this rank's stripe already sits in its slot of the [world * rows, W] buffer
+            dist.all_gather_into_tensor(self.full, self.full[self.rank * self.rows_max:(self.rank + 1) * self.rows_max])
+            return self.full[:self.H]
+        pad = torch.zeros((self.rows_max, self.W), dtype=torch.int8, device=self.device)
+        pad[:self.y1 - self.y0] = self.out
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad)
+        return torch.cat([p[:b - a] for p, (a, b) in zip(parts, self.stripes)], dim=0)
+
+
+_ENGINES: "dict[tuple, TileEngine]" = {}
+
+
+def tile_engine(hls_tile, model: PrithviSeg, window: int, stride: int, batch_size: int, device, **kw) -> TileEngine:
+    """Cached ``TileEngine`` for this (model, raster geometry, constants, sharding)."""
+    if isinstance(hls_tile, np.ndarray):
+        raw_dtype = {np.dtype(np.int16): torch.int16, np.dtype(np.uint16): torch.uint16,
+                     np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}.get(hls_tile.dtype)
+        if raw_dtype is None:
+            raise TypeError(f"unsupported raster dtype {hls_tile.dtype}")
+    else:
+        raw_dtype = hls_tile.dtype
+    if len(hls_tile.shape) != 3:
+        raise ValueError("hls_tile must be [bands, H, W]")
+
+    def freeze(v):
+        return tuple(freeze(x) for x in v) if isinstance(v, (list, tuple)) else v
+
+    key = (id(model), tuple(hls_tile.shape), raw_dtype, window, stride, batch_size, str(device),
+           tuple(sorted((k, freeze(v)) for k, v in kw.items())))
+    eng = _ENGINES.get(key)
+    if eng is None or eng.model is not model:
+        if len(_ENGINES) >= 8:
+            _ENGINES.pop(next(iter(_ENGINES)))
+        eng = TileEngine(model, hls_tile.shape, raw_dtype, window, stride, batch_size, device=device, **kw)
+        _ENGINES[key] = eng
+    return eng
+
+
+@torch.no_grad()
+def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224), stride: int = 224,
+                             batch_size: int = 32, device: str = "gpu", *, mean: Sequence[float],
+                             std: Sequence[float], bands: Optional[Sequence[int]] = None,
+                             constant_multiplier: float = 1.0, no_data_value: Optional[float] = None,
+                             nodata_class: int = -1, rows: Optional[tuple[int, int]] = None,
+                             return_tensor: bool = False, fmask=None, fmask_bits: int = 0,
+                             masking_strategy: str = "each", exchange: Optional[tuple[int, int]] = None):
+    """Overlap-averaged class map of a raw tile [T*C (or more bands), H, W] (int16 | uint16).
+
+    windows -> fused normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4) -> gather-form
+    overlap average + argmax + nodata (kernel 5), through a cached ``TileEngine``.  ``rows=(y0, y1)`` restricts the
+    output to a row stripe and only the windows touching it are computed (multi-GPU halo recompute);
+    per-pixel sums are formed on one rank in fixed order, so any sharding is bit-identical.
+    ``exchange=(rank, world_size)`` (with ``rows`` = ``stripe_rows(H, world_size, rank)``): the rank computes only ITS
+    share of the windows and the ones its stripe needs from other ranks arrive over NCCL send/recv -- no
+    recomputed halo windows, same bits.  Returns int8 [y1-y0, W] (numpy unless ``return_tensor``).
+    """
+    dev = "cuda" if device == "gpu" else device
+    win = int(window_size[0])
+    if window_size[0] != window_size[1] or win != model.image_size:
+        raise ValueError("window must be square and match the model's image_size")
+    if len(hls_tile.shape) != 3:
+        raise ValueError("hls_tile must be [bands, H, W]")
+    H = hls_tile.shape[1]
+    kw = dict(mean=tuple(mean), std=tuple(std), bands=None if bands is None else tuple(bands),
+              constant_multiplier=constant_multiplier, no_data_value=no_data_value, nodata_class=nodata_class,
+              fmask_bits=fmask_bits if fmask is not None else 0, masking_strategy=masking_strategy)
+    if exchange is not None:
+        rank, world = exchange
+        stripes = tuple(stripe_rows(H, world, q) for q in range(world))
+        if rows is not None and tuple(rows) != stripes[rank]:
+            raise ValueError("with exchange=, rows must be stripe_rows(H, world_size, rank)")
+        kw.update(rank=rank, world=world, stripes=stripes)
+    elif rows is not None:
+        kw.update(stripes=(tuple(rows),))
+    eng = tile_engine(hls_tile, model, win, stride, batch_size, dev, **kw)
+    out = eng.run(hls_tile, fmask=fmask, gather=False).clone()
+    return out if return_tensor else out.cpu().numpy()
 
 
 @torch.no_grad()
 def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, world_size: int,
-                                     halo_recompute: bool = False, **kw):
-    """One process per GPU: every rank runs the model on its share of the window rows, the rows that straddle a
-    stripe boundary are exchanged over NCCL send/recv, each rank stitches its output row stripe, and the int8
-    stripes are all-gathered.  ``halo_recompute=True`` is the collective-free alternative (every rank recomputes
-    the windows that touch its stripe).  Either way the result is bit-identical to one GPU.  Returns [H, W]."""
-    H = hls_tile.shape[1]
-    y0, y1 = stripe_rows(H, world_size, rank)
+                                     halo_recompute: bool = False, copy: bool = True, **kw):
+    """One process per GPU: every rank runs the model on its share of the windows, the windows a stripe needs from
+    other ranks are exchanged over NCCL send/recv, each rank stitches its output row stripe, and the int8 stripes
+    are all-gathered in place.  ``halo_recompute=True`` is the collective-free alternative (every rank recomputes
+    the windows that touch its stripe).  Either way the result is bit-identical to one GPU.  Returns [H, W] int8 on
+    the device (``copy=False``: a view of the engine's buffer, overwritten by the next tile)."""
     kw = dict(kw)
-    kw["rows"] = (y0, y1)
-    kw["return_tensor"] = True
-    if world_size > 1 and not halo_recompute:
-        kw["exchange"] = (rank, world_size)
-    local = sliding_window_inference(hls_tile, model, **kw)
-    return gather_stripes(local, H, world_size)
+    window_size = kw.pop("window_size", (224, 224))
+    stride, batch_size = kw.pop("stride", 224), kw.pop("batch_size", 32)
+    device = kw.pop("device", "gpu")
+    fmask = kw.pop("fmask", None)
+    kw.pop("return_tensor", None)
+    dev = "cuda" if device == "gpu" else device
+    win = int(window_size[0])
+    if window_size[0] != window_size[1] or win != model.image_size:
+        raise ValueError("window must be square and match the model's image_size")
+    ekw = dict(mean=tuple(kw.pop("mean")), std=tuple(kw.pop("std")),
+               bands=None if kw.get("bands") is None else tuple(kw["bands"]),
+               constant_multiplier=kw.pop("constant_multiplier", 1.0), no_data_value=kw.pop("no_data_value", None),
+               nodata_class=kw.pop("nodata_class", -1), fmask_bits=kw.pop("fmask_bits", 0) if fmask is not None else 0,
+               masking_strategy=kw.pop("masking_strategy", "each"), rank=rank, world=world_size,
+               halo_recompute=halo_recompute)
+    kw.pop("bands", None)
+    kw.pop("fmask_bits", None)
+    if kw:
+        raise TypeError(f"unexpected arguments {sorted(kw)}")
+    eng = tile_engine(hls_tile, model, win, stride, batch_size, dev, **ekw)
+    out = eng.run(hls_tile, fmask=fmask, gather=True)
+    return out.clone() if copy else out
 
 
 # --------------------------------------------------------------------------- host <-> device pipeline
 class ChipPipeline:
     """The call a user makes for a stream of raw chip batches held in HOST memory.
 
-    ``run(batches)``: for every [B, T*C, 224, 224] int16/uint16 host array -> int8 class masks
-    [B, 224, 224] on the host.  Per step: pinned H2D copy of the raw integers (2 B/element, not
-    the 4 B/element float tensor the reference ships, instageo/model/infer_utils.py:93), fused
-    normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4, argmax fused) -> D2H of the int8 masks
-    (1 B/pixel instead of float logits, :99-101).  Copies run on a side stream and overlap the
-    previous step's compute (double buffering); results are identical to the unpipelined path.
+    ``run(batches)``: for every [b, n_src_bands, 224, 224] int16/uint16 host array (b <= ``batch``; the last batch of
+    a set may be short) -> int8 class masks [b, 224, 224] on the host.  Per step: pinned H2D copy of the raw
+    integers (2 B/element, not the 4 B/element float tensor the reference ships,
+    instageo/model/infer_utils.py:93), fused normalise/mask (kernel 1) -> PrithviSeg (kernels 2-4, argmax fused,
+    one CUDA-graph launch) -> D2H of the int8 masks (1 B/pixel instead of float logits, :99-101).  Copies run on a
+    side stream and overlap the previous step's compute (double buffering); results are identical to the
+    unpipelined path.
+
+    ``consume(masks)`` receives a VIEW of a reused pinned buffer: it is valid only for the duration of the call
+    (copy it to keep it).
     """
 
     def __init__(self, model: PrithviSeg, spec: ops.PreprocessSpec, batch: int, device="cuda",
                  raw_dtype=torch.int16):
         self.model, self.spec, self.batch = model, spec, batch
         self.device = torch.device(device)
-        S, tc = model.image_size, spec.T * spec.C
-        n_src = max(spec.bands) + 1
-        self.h_in = [torch.empty((batch, n_src, S, S), dtype=torch.int16).pin_memory() for _ in range(2)]
-        self.d_in = [torch.empty((batch, n_src, S, S), dtype=torch.int16, device=self.device) for _ in range(2)]
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        S = model.image_size
+        self.n_src = max(spec.bands) + 1
+        self.h_in = [torch.empty((batch, self.n_src, S, S), dtype=torch.int16).pin_memory() for _ in range(2)]
+        self.d_in = [torch.empty((batch, self.n_src, S, S), dtype=torch.int16, device=self.device) for _ in range(2)]
         self.h_out = [torch.empty((batch, S, S), dtype=torch.int8).pin_memory() for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(self.device)
-        self.in_ready = [torch.cuda.Event() for _ in range(2)]
-        self.in_free = [torch.cuda.Event() for _ in range(2)]
+        self.in_ready = [torch.cuda.Event() for _ in range(2)]    # H2D of the slot has finished (copy stream)
+        self.in_free = [torch.cuda.Event() for _ in range(2)]     # the slot's device input has been consumed
         self.out_ready = [torch.cuda.Event() for _ in range(2)]
+        self.staged = [False, False]  # h_in[slot] is the source of an H2D copy that may still be in flight
+        self.n_in_slot = [0, 0]
         self.raw_dtype = raw_dtype
-        self.h2d_bytes = batch * n_src * S * S * 2
+        self.h2d_bytes = batch * self.n_src * S * S * 2
         self.d2h_bytes = batch * S * S
         model.eval()
 
@@ -347,50 +558,69 @@ class ChipPipeline:
         src = host_batch if isinstance(host_batch, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host_batch))
         if src.dtype == torch.uint16:
             src = src.view(torch.int16)
+        if src.dtype != torch.int16:
+            raise TypeError(f"ChipPipeline: host batches must be int16 / uint16, got {src.dtype}")
+        S = self.model.image_size
+        if src.dim() != 4 or tuple(src.shape[1:]) != (self.n_src, S, S):
+            raise ValueError(f"ChipPipeline: host batch must be [b, {self.n_src}, {S}, {S}] "
+                             f"(max(bands) + 1 = {self.n_src} source bands), got {tuple(src.shape)}")
+        b = src.shape[0]
+        if not 1 <= b <= self.batch:
+            raise ValueError(f"ChipPipeline: batch of {b} chips, expected 1..{self.batch}")
+        self.n_in_slot[slot] = b
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.in_free[slot])
             if src.is_pinned():
-                self.d_in[slot].copy_(src, non_blocking=True)
+                self.d_in[slot][:b].copy_(src, non_blocking=True)
             else:
-                self.h_in[slot].copy_(src)
-                self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
+                # The staging buffer is the source of the H2D copy of batch i-2 (same slot).  That DMA is ordered on
+                # the copy STREAM only; the host must wait for it before overwriting the pinned memory, or a slow
+                # copy (tiny model, slow PCIe) ships a half-overwritten batch.
+                if self.staged[slot]:
+                    self.in_ready[slot].synchronize()
+                self.h_in[slot][:b].copy_(src)
+                self.d_in[slot][:b].copy_(self.h_in[slot][:b], non_blocking=True)
+                self.staged[slot] = True
             self.in_ready[slot].record(self.copy_stream)
 
     def _compute(self, slot: int) -> None:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.in_ready[slot])
-        raw = self.d_in[slot] if self.raw_dtype == torch.int16 else self.d_in[slot].view(torch.uint16)
+        b = self.n_in_slot[slot]
+        raw = self.d_in[slot][:b] if self.raw_dtype == torch.int16 else self.d_in[slot][:b].view(torch.uint16)
         pre = ops.preprocess(raw, self.spec, win=self.model.image_size, want_f32=False, want_patches=True)
         amax = self.model.forward_patches(pre["patches"], want_logits=False, want_argmax=True)[1]
         self.in_free[slot].record(cur)
-        self.h_out[slot].copy_(amax, non_blocking=True)
+        self.h_out[slot][:b].copy_(amax, non_blocking=True)
         self.out_ready[slot].record(cur)
 
     @torch.no_grad()
     def run(self, batches, consume: Optional[Callable] = None) -> int:
-        """Process an iterable of host batches; ``consume(np.ndarray int8 [B,224,224])`` per batch."""
+        """Process an iterable of host batches; ``consume(np.ndarray int8 [b,224,224])`` per batch (a view that is
+        only valid during the call)."""
         n, pending = 0, None
         it = iter(batches)
         nxt = next(it, None)
-        if nxt is not None:
-            self._upload(0, nxt)
-        i = 0
-        while nxt is not None:
-            slot = i & 1
-            cur_batch = nxt
-            nxt = next(it, None)
+        with torch.cuda.device(self.device):
             if nxt is not None:
-                self._upload(slot ^ 1, nxt)   # overlaps with the compute below
-            self._compute(slot)
+                self._upload(0, nxt)
+            i = 0
+            while nxt is not None:
+                slot = i & 1
+                cur_batch = nxt
+                nxt = next(it, None)
+                if nxt is not None:
+                    self._upload(slot ^ 1, nxt)   # overlaps with the compute below
+                self._compute(slot)
+                if pending is not None:
+                    self.out_ready[pending[0]].synchronize()
+                    if consume is not None:
+                        consume(self.h_out[pending[0]][:pending[1]].numpy())
+                pending = (slot, self.n_in_slot[slot])
+                n += len(cur_batch)
+                i += 1
             if pending is not None:
-                self.out_ready[pending].synchronize()
+                self.out_ready[pending[0]].synchronize()
                 if consume is not None:
-                    consume(self.h_out[pending].numpy())
-            pending = slot
-            n += len(cur_batch)
-            i += 1
-        if pending is not None:
-            self.out_ready[pending].synchronize()
-            if consume is not None:
-                consume(self.h_out[pending].numpy())
+                    consume(self.h_out[pending[0]][:pending[1]].numpy())
         return n

@@ -106,15 +106,17 @@ class RunningConfusionMatrix:
         if t.shape != p.shape:
             raise ValueError("y_true and y_pred shapes differ.")
         if p.dtype != torch.int8:
-            if p.numel() and (int(p.max()) > 127 or int(p.min()) < -128):
-                raise ValueError("prediction outside [0, num_classes)")
-            p = p.to(torch.int8)
+            # No host round trip for the range check (the reference raises inside update; here an out-of-range
+            # prediction stays out of range after the clamp -- num_classes <= 127 -- and lands in the kernel's
+            # out-of-range counter, which _sync() turns into the same ValueError at the first read-back).
+            if self.num_classes > 127:
+                raise ValueError("non-int8 predictions need num_classes <= 127")
+            p = p.clamp(-1, 127).to(torch.int8)
         p = p.contiguous()
         has_ign = self.ignore_index is not None
-        _lib.check(_lib.load().ig_confusion_update(
-            p.data_ptr(), t.data_ptr(), _LABEL_DTYPES[t.dtype], t.numel(), self.num_classes, int(has_ign),
-            int(self.ignore_index) if has_ign else 0, self._mat.data_ptr(), self._cnt.data_ptr(),
-            _lib.current_stream()))
+        _lib.call("ig_confusion_update", self.device,
+                  p.data_ptr(), t.data_ptr(), _LABEL_DTYPES[t.dtype], t.numel(), self.num_classes, int(has_ign),
+                  int(self.ignore_index) if has_ign else 0, self._mat.data_ptr(), self._cnt.data_ptr())
 
     def _sync(self):
         cnt = self._cnt.cpu().numpy()
@@ -192,10 +194,10 @@ class RunningAUC:
         if s.dim() != 2 or s.shape[1] != self.num_classes:
             raise ValueError("Second dim of y_score must equal num_classes.")
         s = s.contiguous()
-        _lib.check(_lib.load().ig_auc_update(
-            s.data_ptr(), _lib.IG_F32 if s.dtype == torch.float32 else _lib.IG_F64, s.shape[0], self.num_classes,
-            t.data_ptr(), _LABEL_DTYPES[t.dtype], self.n_bins, float(self.min_score), float(self.max_score),
-            self._pos.data_ptr(), self._neg.data_ptr(), _lib.current_stream()))
+        _lib.call("ig_auc_update", self.device,
+                  s.data_ptr(), _lib.IG_F32 if s.dtype == torch.float32 else _lib.IG_F64, s.shape[0], self.num_classes,
+                  t.data_ptr(), _LABEL_DTYPES[t.dtype], self.n_bins, float(self.min_score), float(self.max_score),
+                  self._pos.data_ptr(), self._neg.data_ptr())
 
     @property
     def pos_hist(self) -> np.ndarray:
@@ -249,12 +251,12 @@ def segmentation_eval_update(logits: torch.Tensor, labels: torch.Tensor, confusi
         return
     cnt = confusion._cnt if confusion is not None else torch.zeros(2, dtype=torch.int64, device=logits.device)
     has_ign = ignore_index is not None
-    _lib.check(_lib.load().ig_seg_metrics_update(
-        logits.data_ptr(), B, nc, H * W, lab.data_ptr(), _LABEL_DTYPES[lab.dtype], int(has_ign),
-        int(ignore_index) if has_ign else 0, _lib.ptr(confusion._mat if confusion is not None else None),
-        cnt.data_ptr(), auc.n_bins if auc is not None else 2, float(auc.min_score) if auc is not None else 0.0,
-        float(auc.max_score) if auc is not None else 1.0, _lib.ptr(auc._pos if auc is not None else None),
-        _lib.ptr(auc._neg if auc is not None else None), _lib.current_stream()))
+    _lib.call("ig_seg_metrics_update", logits.device,
+              logits.data_ptr(), B, nc, H * W, lab.data_ptr(), _LABEL_DTYPES[lab.dtype], int(has_ign),
+              int(ignore_index) if has_ign else 0, _lib.ptr(confusion._mat if confusion is not None else None),
+              cnt.data_ptr(), auc.n_bins if auc is not None else 2, float(auc.min_score) if auc is not None else 0.0,
+              float(auc.max_score) if auc is not None else 1.0, _lib.ptr(auc._pos if auc is not None else None),
+              _lib.ptr(auc._neg if auc is not None else None))
 
 
 class RunningRegressionMetrics:
@@ -278,10 +280,9 @@ class RunningRegressionMetrics:
         if x.shape != y.shape:
             raise ValueError("y_true and y_pred shapes differ.")
         has_ign = ignore_value is not None
-        _lib.check(_lib.load().ig_regression_update(
-            x.data_ptr(), y.data_ptr(), x.numel(), int(has_ign), float(ignore_value) if has_ign else 0.0,
-            float(self.ee_bias), float(self.ee_coef), self._sums.data_ptr(), self._counts.data_ptr(),
-            _lib.current_stream()))
+        _lib.call("ig_regression_update", self.device,
+                  x.data_ptr(), y.data_ptr(), x.numel(), int(has_ign), float(ignore_value) if has_ign else 0.0,
+                  float(self.ee_bias), float(self.ee_coef), self._sums.data_ptr(), self._counts.data_ptr())
 
     def _state(self) -> dict:
         s, c = self._sums.cpu().numpy(), self._counts.cpu().numpy()

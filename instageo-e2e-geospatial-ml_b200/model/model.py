@@ -205,6 +205,8 @@ class PrithviSeg(nn.Module):
         self._engine_sig = None
         self._engine_device = None
         self._workspaces: dict = {}
+        self._sig_tensors: Optional[list] = None
+        self._tap_buf: Optional[torch.Tensor] = None
         self.eval()
 
     # ------------------------------------------------------------------ weights
@@ -245,7 +247,22 @@ class PrithviSeg(nn.Module):
 
     # ------------------------------------------------------------------ engine
     def _signature(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        """(address, version) of every parameter / buffer.  The tensor list is cached: building ``state_dict()`` on
+        every forward cost 188-332 prefix-joined dictionary entries of host work per step.  ``_apply`` (``.to()``,
+        ``.cuda()``, ``.half()``) and ``load_state_dict`` drop the cache; in-place edits bump ``_version``."""
+        if self._sig_tensors is None:
+            self._sig_tensors = list(self.state_dict(keep_vars=True).values())
+        return tuple((t.data_ptr(), t._version) for t in self._sig_tensors)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._sig_tensors = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._sig_tensors = None
+        out = super().load_state_dict(*args, **kwargs)
+        self._sig_tensors = None
+        return out
 
     def _destroy_engine(self) -> None:
         if getattr(self, "_engine", None):
@@ -255,6 +272,7 @@ class PrithviSeg(nn.Module):
                 pass
         self._engine = None
         self._workspaces = {}
+        self._tap_buf = None
 
     def __del__(self):
         try:
@@ -277,8 +295,8 @@ class PrithviSeg(nn.Module):
                 _lib.check(lib.ig_model_create(C.byref(cfg), C.byref(handle)))
             self._engine = handle.value
             self._engine_device = device
-        stream = _lib.current_stream()
         with torch.cuda.device(device):
+            stream = _lib.current_stream(device)
             for key, t in self.state_dict().items():
                 if not t.is_floating_point():
                     continue  # num_batches_tracked
@@ -299,13 +317,18 @@ class PrithviSeg(nn.Module):
         need = _lib.load().ig_model_workspace_bytes(self._engine, batch) + 1024
         ws = self._workspaces.get(device)
         if ws is None or ws.numel() < need:
+            # the engine caches plans / graphs / cleared borders per workspace address: the old block is about to be
+            # freed (and its address may be handed to someone else), so that cache goes with it
+            _lib.check(_lib.load().ig_model_reset_cache(self._engine))
+            self._workspaces = {}
+            ws = None
             ws = torch.zeros(need, dtype=torch.uint8, device=device)
             self._workspaces = {device: ws}
         off = (-ws.data_ptr()) % 1024
         return ws[off:]
 
     def _run(self, x: torch.Tensor, x_dtype: int, batch: int, want_logits: bool, want_argmax: bool,
-             want_feats: bool):
+             want_feats: bool, out_logits: Optional[torch.Tensor] = None, out_argmax: Optional[torch.Tensor] = None):
         if self.training:
             raise RuntimeError("instageo_b200.PrithviSeg is inference-only: call model.eval() first")
         if not x.is_cuda:
@@ -315,15 +338,53 @@ class PrithviSeg(nn.Module):
         lib = _lib.load()
         S, nc, T = self.image_size, self.num_classes, self.temporal_step
         ws = self._workspace(batch, dev)
-        logits = torch.empty((batch, nc, S, S), dtype=torch.float32, device=dev) if want_logits else None
-        amax = torch.empty((batch, S, S), dtype=torch.int8, device=dev) if (want_argmax and nc > 1) else None
+        logits = amax = None
+        if want_logits:
+            logits = out_logits if out_logits is not None else torch.empty((batch, nc, S, S), dtype=torch.float32, device=dev)
+            if logits.dtype != torch.float32 or not logits.is_contiguous() or tuple(logits.shape) != (batch, nc, S, S) \
+                    or logits.device != dev:
+                raise ValueError(f"out_logits must be a contiguous float32 [{batch}, {nc}, {S}, {S}] tensor on {dev}")
+        if want_argmax and nc > 1:
+            amax = out_argmax if out_argmax is not None else torch.empty((batch, S, S), dtype=torch.int8, device=dev)
+            if amax.dtype != torch.int8 or not amax.is_contiguous() or tuple(amax.shape) != (batch, S, S) \
+                    or amax.device != dev:
+                raise ValueError(f"out_argmax must be a contiguous int8 [{batch}, {S}, {S}] tensor on {dev}")
         feats = (torch.empty((batch, self.embed_dims[0], S // 16, S // 16), dtype=torch.float32, device=dev)
                  if want_feats else None)
         with torch.cuda.device(dev):
+            self._attach_taps(batch, dev)
             _lib.check(lib.ig_model_forward(self._engine, x.data_ptr(), x_dtype, batch, _lib.ptr(logits),
                                             _lib.ptr(amax), _lib.ptr(feats), ws.data_ptr(), ws.numel(),
-                                            _lib.current_stream()))
+                                            _lib.current_stream(dev)))
         return logits, amax, feats
+
+    # ------------------------------------------------------------------ parity taps
+    def enable_taps(self, on: bool = True) -> None:
+        """Record the encoder taps of every following forward ('embed', 'block<i>', 'tokens'; test use: the forward
+        then runs kernel by kernel with one device copy per block instead of replaying its CUDA graph)."""
+        self._taps_on = bool(on)
+        if not on:
+            self._tap_buf = None
+            if self._engine:
+                _lib.check(_lib.load().ig_model_set_tap_buffer(self._engine, None, 0))
+
+    def _attach_taps(self, batch: int, dev: torch.device) -> None:
+        if not getattr(self, "_taps_on", False):
+            return
+        enc = self.prithvi_encoder
+        n = (len(enc.blocks) + 2) * batch * (1 + self.temporal_step * (self.image_size // 16) ** 2) * enc.embed_dim
+        if self._tap_buf is None or self._tap_buf.numel() < n or self._tap_buf.device != dev:
+            self._tap_buf = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().ig_model_set_tap_buffer(self._engine, self._tap_buf.data_ptr(), self._tap_buf.numel()))
+
+    def graph_status(self) -> dict:
+        """{'enabled', 'last_forward_was_graph', 'kernels_in_graph', 'note'} of the engine's CUDA-graph replay."""
+        if not self._engine:
+            return {"enabled": False, "last_forward_was_graph": False, "kernels_in_graph": 0, "note": "no engine yet"}
+        last, nk, note = C.c_int(0), C.c_int(0), C.create_string_buffer(256)
+        en = _lib.load().ig_model_graph_status(self._engine, C.byref(last), C.byref(nk), note, 256)
+        return {"enabled": bool(en), "last_forward_was_graph": bool(last.value), "kernels_in_graph": nk.value,
+                "note": note.value.decode("utf-8", "replace")}
 
     def _check_img(self, img: torch.Tensor) -> torch.Tensor:
         T, S = self.temporal_step, self.image_size
@@ -371,31 +432,35 @@ class PrithviSeg(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(_lib.load().ig_model_predict_proba(self._engine, img.data_ptr(), _lib.IG_F32, B,
                                                           prob.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                          _lib.current_stream()))
+                                                          _lib.current_stream(dev)))
         return prob
 
     @torch.no_grad()
-    def forward_patches(self, patches: torch.Tensor, want_logits: bool = True, want_argmax: bool = False):
+    def forward_patches(self, patches: torch.Tensor, want_logits: bool = True, want_argmax: bool = False,
+                        out_logits: Optional[torch.Tensor] = None, out_argmax: Optional[torch.Tensor] = None):
         """Production entry: tubelet rows written by the fused preprocessing kernel
-        (``ops.preprocess(..., want_patches=True)``), bf16 [B*T*196, 1536]."""
+        (``ops.preprocess(..., want_patches=True)``), bf16 [B*T*196, 1536].  ``out_logits`` / ``out_argmax``: write
+        into the caller's buffers (e.g. a slice of a tile's window-logit array) instead of new tensors."""
         rows = self.temporal_step * (self.image_size // 16) ** 2
         if patches.dtype != torch.bfloat16 or patches.dim() != 2 or patches.shape[1] != IN_CHANS * 256 \
                 or patches.shape[0] % rows:
             raise ValueError(f"patches must be bf16 [B*{rows}, {IN_CHANS * 256}]")
         logits, amax, _ = self._run(patches.contiguous(), _lib.IG_BF16, patches.shape[0] // rows, want_logits,
-                                    want_argmax, False)
+                                    want_argmax, False, out_logits, out_argmax)
         return logits, amax
 
     def launches_per_forward(self) -> int:
         return int(_lib.load().ig_model_launches_per_forward(self._engine)) if self._engine else 0
 
     def debug_tap(self, name: str, batch: int, shape) -> torch.Tensor:
-        """Intermediate activation of the last forward (parity tests): 'x', 'feat', 'convt<i>', 'stage<i>'."""
+        """Intermediate activation of the last forward (parity tests): 'x', 'feat', 'convt<i>', 'stage<i>', and --
+        after ``enable_taps()`` -- 'embed', 'block<i>', 'tokens' ([B, N, D])."""
         dev = self._engine_device
         ws = self._workspace(batch, dev)
         out = torch.empty(tuple(shape), dtype=torch.float32, device=dev)
-        _lib.check(_lib.load().ig_model_debug_tap(self._engine, name.encode(), batch, ws.data_ptr(), out.data_ptr(),
-                                                  out.numel(), _lib.current_stream()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ig_model_debug_tap(self._engine, name.encode(), batch, ws.data_ptr(),
+                                                      out.data_ptr(), out.numel(), _lib.current_stream(dev)))
         return out
 
 

@@ -93,7 +93,7 @@ def test_interface_behaviour(cuda_dev):
     m.load_state_dict(sd2)
     ref = P.prithvi_seg_forward(x.cpu(), sd2, 4, 1)
     assert (m(x).cpu() - ref).abs().max().item() < TOL
-    assert m.launches_per_forward() == 3 + 7 * 1 + 1 + 5 + 8
+    assert m.launches_per_forward() == 3 + 7 * 1 + 1 + 8
 
 
 def test_fused_preprocess_to_model(cuda_dev):
@@ -180,3 +180,128 @@ def test_full_depth_configs_vs_oracle(cuda_dev, variant, T, nc, B):
         print(f"{variant} T={T} nc={nc} stress={stress}: max-abs {eps:.3e} of {scale:.2f}, tie-excluded pixels {excluded:.4f}")
         del m
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("variant,T,nc,depth,B", [("prithvi_eo_tiny", 1, 2, 4, 2), ("prithvi_eo_v1_100", 3, 13, 3, 1),
+                                                  ("prithvi_eo_v2_300", 1, 2, 2, 2)])
+def test_per_block_taps_vs_oracle(cuda_dev, variant, T, nc, depth, B):
+    """SURVEY.md Appendix F 'patch-embed, per-block': the residual stream after the patch embed, after every block
+    and after the final LayerNorm against the fp32 oracle's taps (bf16 GEMM operands, f32 accumulation / residual:
+    tolerance 1e-2 of the tap's own scale, written here)."""
+    m, sd = _build(variant, T, nc, depth, cuda_dev, stress=True)
+    x = torch.randn(B, 6, T, 224, 224, generator=torch.Generator().manual_seed(40 + B))
+    taps = {}
+    ref = P.prithvi_seg_forward(x, sd, P.VARIANTS[variant][2], T, taps=taps)
+    m.enable_taps(True)
+    y = m(x.to(cuda_dev))
+    assert not m.graph_status()["last_forward_was_graph"]
+    D, N = P.VARIANTS[variant][0], 1 + T * 196
+    worst = 0.0
+    for name in ["embed"] + [f"block{i}" for i in range(depth)] + ["tokens"]:
+        got = m.debug_tap(name, B, (B, N, D)).cpu()
+        want = taps[name]
+        rel = (got - want).abs().max().item() / max(want.abs().max().item(), 1e-6)
+        worst = max(worst, rel)
+        assert rel < 1e-2, f"{name}: max-abs error {rel:.3e} of the tap's scale"
+    print(f"{variant} T={T}: worst per-block relative error {worst:.3e}")
+    assert (y.cpu() - ref).abs().max().item() < TOL
+    with pytest.raises(Exception):
+        m.debug_tap(f"block{depth}", B, (B, N, D))
+    m.enable_taps(False)
+    y2 = m(x.to(cuda_dev))
+    assert torch.equal(y, y2)  # the taps do not change the result
+
+
+def test_graph_replay_follows_caller_pointers(cuda_dev):
+    """The production entry replays a CUDA graph; x / logits / argmax pointers that change between calls are patched
+    into the graph, and the result is bit-identical to the kernel-by-kernel path (the f32 entry)."""
+    from instageo_b200 import ops
+    from oracle import preprocess as OP
+    from conftest import FLOOD_MEAN, FLOOD_STD
+    m, sd = _build("prithvi_eo_tiny", 1, 2, 2, cuda_dev)
+    spec = ops.PreprocessSpec(FLOOD_MEAN, FLOOD_STD, 1, None, 1e-4, None, cuda_dev)
+    raws = [torch.from_numpy(OP.synth_chips(3, 1, seed=s)).to(cuda_dev) for s in (1, 2)]
+    pres = [ops.preprocess(r, spec, want_f32=True, want_patches=True) for r in raws]
+    keep = []
+    for rep in range(3):
+        for pre in pres:
+            la, aa = m.forward_patches(pre["patches"], want_logits=True, want_argmax=True)
+            st = m.graph_status()
+            assert st["enabled"], st["note"]
+            assert st["last_forward_was_graph"] and st["kernels_in_graph"] == m.launches_per_forward() - 1
+            keep.append((la, aa, pre))  # outputs stay alive: every call gets NEW output addresses
+    for la, aa, pre in keep:
+        lb = m(pre["f32"])
+        assert torch.equal(la, lb) and torch.equal(aa.long(), lb.argmax(1))
+    # argmax-only graph (another flag set) next to the first one, and a second batch size on the same workspace
+    a1 = m.forward_patches(pres[0]["patches"], want_logits=False, want_argmax=True)[1]
+    assert torch.equal(a1, keep[0][1])
+    rows = 196
+    a2 = m.forward_patches(pres[1]["patches"][:2 * rows], want_logits=False, want_argmax=True)[1]
+    assert torch.equal(a2, keep[1][1][:2])
+    a3 = m.forward_patches(pres[0]["patches"], want_logits=False, want_argmax=True)[1]
+    assert torch.equal(a3, keep[0][1])
+
+
+def test_timed_configuration_multiwave_vs_oracle(cuda_dev):
+    """BASELINE.json configs[1] as bench.py times it: V1-100M, T=3, 13 classes, FULL depth, through
+    preprocess -> tubelet rows -> forward_patches(argmax) at B = 64 (M = 37 696 token rows: several waves of the
+    persistent GEMMs and of the attention kernel).  The first 16 chips are also run as their own batch (still
+    multi-wave) and compared with the fp32 oracle; the B = 64 result must contain them bit for bit."""
+    from instageo_b200 import ops
+    from oracle import preprocess as OP
+    from conftest import CROP_MEAN, CROP_STD
+    variant, T, nc = "prithvi_eo_v1_100", 3, 13
+    m, sd = _build(variant, T, nc, -1, cuda_dev, seed=0, stress=True)
+    raw = OP.synth_chips(64, T, seed=1042, nodata=None)
+    spec = ops.PreprocessSpec(CROP_MEAN, CROP_STD, T, None, 1.0, None, cuda_dev)
+    d_raw = torch.from_numpy(raw).to(cuda_dev)
+    pre64 = ops.preprocess(d_raw, spec, want_f32=False, want_patches=True)
+    l64, a64 = m.forward_patches(pre64["patches"], want_logits=True, want_argmax=True)
+    pre16 = ops.preprocess(d_raw[:16], spec, want_f32=False, want_patches=True)
+    l16, a16 = m.forward_patches(pre16["patches"], want_logits=True, want_argmax=True)
+    assert torch.equal(l64[:16], l16) and torch.equal(a64[:16], a16)
+    assert torch.equal(a64.long(), l64.argmax(1))
+    n_ref = 4  # oracle cost: ~1 s per chip on the host cores
+    xr = np.stack([OP.preprocess_chip(r, None, 1.0, CROP_MEAN, CROP_STD, T, None)[0] for r in raw[:n_ref]])
+    ref = P.prithvi_seg_forward(torch.from_numpy(xr), sd, P.VARIANTS[variant][2], T)
+    eps = (l64[:n_ref].cpu() - ref).abs().max().item()
+    assert eps < TOL, f"B=64 logits max-abs {eps}"
+    # the last chips of the batch sit in the last, partially filled wave: check them as well
+    xr2 = np.stack([OP.preprocess_chip(r, None, 1.0, CROP_MEAN, CROP_STD, T, None)[0] for r in raw[62:]])
+    ref2 = P.prithvi_seg_forward(torch.from_numpy(xr2), sd, P.VARIANTS[variant][2], T)
+    eps2 = (l64[62:].cpu() - ref2).abs().max().item()
+    assert eps2 < TOL, f"B=64 (last chips) logits max-abs {eps2}"
+    excluded = _argmax_check(a64[:n_ref], ref, max(eps, eps2))
+    print(f"B=64 timed configuration: max-abs {max(eps, eps2):.3e}, tie-excluded {excluded:.4f}")
+
+
+def test_chip_pipeline_unpinned_sources_and_short_last_batch(cuda_dev):
+    """ChipPipeline.run with pageable (non-pinned) host batches -- the staging buffer of a slot must not be
+    overwritten while its previous H2D copy is in flight (tiny model: the copies are the slow part) -- and with a
+    last batch shorter than ``batch``; every mask equals the unpipelined path's."""
+    from instageo_b200 import ops
+    from instageo_b200.model.infer_utils import ChipPipeline
+    from oracle import preprocess as OP
+    from conftest import FLOOD_MEAN, FLOOD_STD
+    m, sd = _build("prithvi_eo_tiny", 1, 2, 0, cuda_dev)
+    spec = ops.PreprocessSpec(FLOOD_MEAN, FLOOD_STD, 1, None, 1e-4, None, cuda_dev)
+    B = 8
+    sizes = [B] * 9 + [3, 1]
+    batches = [OP.synth_chips(n, 1, seed=100 + i) for i, n in enumerate(sizes)]   # numpy: pageable memory
+    want = []
+    for raw in batches:
+        pre = ops.preprocess(torch.from_numpy(raw).to(cuda_dev), spec, want_f32=False, want_patches=True)
+        want.append(m.forward_patches(pre["patches"], want_logits=False, want_argmax=True)[1].cpu().numpy())
+    pipe = ChipPipeline(m, spec, B, cuda_dev)
+    got = []
+    n = pipe.run(batches, consume=lambda a: got.append(a.copy()))
+    assert n == sum(sizes) and [g.shape[0] for g in got] == sizes
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    # pinned sources take the direct path; same masks
+    got2 = []
+    pipe.run([torch.from_numpy(b).pin_memory() for b in batches], consume=lambda a: got2.append(a.copy()))
+    assert all(np.array_equal(g, w) for g, w in zip(got2, want))
+    with pytest.raises(ValueError):
+        pipe.run([batches[0][:, :5]])

@@ -54,6 +54,17 @@ def test_stripes_equal_full_and_halo(cuda_dev, stitch_path):
             parts.append(ops.stitch(sub, ys, xs, H, W, y0=y0, y1=y1, win_base=lo * len(xs))["class_map"])
         assert torch.equal(torch.cat(parts), full)
     assert ops.stitch(lg, ys, xs, H, W, y0=10, y1=10)["class_map"].shape == (0, W)
+    # the nodata map of a stripe holds the stripe's own rows (what ig_nodata_map writes); the whole map is accepted too
+    nd = torch.rand((H, W), device=cuda_dev) < 0.1
+    full_nd = ops.stitch(lg, ys, xs, H, W, nodata_px=nd, nodata_class=-7)["class_map"]
+    assert bool((full_nd[nd] == -7).all()) and torch.equal(full_nd[~nd], full[~nd])
+    for (y0, y1) in ((0, 233), (233, 467), (467, 700), (5, 6)):
+        lo, hi = IU.windows_for_rows(ys, win, y0, y1)
+        sub = lg[lo * len(xs): hi * len(xs)].contiguous()
+        a = ops.stitch(sub, ys, xs, H, W, y0=y0, y1=y1, win_base=lo * len(xs), nodata_px=nd[y0:y1].contiguous(),
+                       nodata_class=-7)["class_map"]
+        b = ops.stitch(sub, ys, xs, H, W, y0=y0, y1=y1, win_base=lo * len(xs), nodata_px=nd, nodata_class=-7)["class_map"]
+        assert torch.equal(a, full_nd[y0:y1]) and torch.equal(b, full_nd[y0:y1])
 
 
 def test_full_tile_properties(cuda_dev):

@@ -53,6 +53,97 @@ def test_tile_vs_oracle_and_sharding(cuda_dev):
     assert np.array_equal(got2[:224, :224], m.predict(x00)[0].cpu().numpy())
 
 
+@pytest.mark.parametrize("H,W,dtype,cm,nodata", [(500, 460, np.int16, 1.0, -9999), (300, 333, np.uint16, 1.0, 0),
+                                                 (229, 250, np.int16, 1e-4, -0.9999), (224, 224, np.int16, 1.0, None),
+                                                 (260, 1029, np.int16, 1.0, 12.5)])
+def test_nodata_map_vs_oracle_and_window_masks(cuda_dev, H, W, dtype, cm, nodata):
+    """ig_nodata_map (tile-level 'any selected band is nodata') == the oracle's tile_nodata_px == the per-window
+    pixel masks of kernel 1 scattered back (the previous implementation), incl. band subsets, a non-unit multiplier
+    (the comparison happens after the float64 product, F10), widths that are not multiples of 8, row ranges."""
+    from instageo_b200 import ops
+    from instageo_b200.model import infer_utils as IU
+    rng = np.random.default_rng(H * 7 + W)
+    nb, bands = 8, [7, 0, 2, 3, 5, 1]
+    lo = 0 if dtype == np.uint16 else -3
+    tile = rng.integers(lo, 6, size=(nb, H, W)).astype(dtype)
+    if nodata is not None and float(nodata).is_integer():
+        tile[rng.random(tile.shape) < 0.02] = dtype(nodata)
+    if cm != 1.0:
+        tile[rng.random(tile.shape) < 0.02] = -9999     # -9999 * 1e-4 == -0.9999 in float64
+    spec = ops.PreprocessSpec(FLOOD_MEAN, FLOOD_STD, 1, bands, cm, nodata, cuda_dev)
+    d = torch.from_numpy(tile.view(np.int16) if dtype == np.uint16 else tile).to(cuda_dev)
+    if dtype == np.uint16:
+        d = d.view(torch.uint16)
+    want = OS.tile_nodata_px(tile, bands, cm, nodata)
+    got = ops.nodata_map(d, spec).cpu().numpy()
+    assert got.shape == (H, W) and np.array_equal(got, want)
+    if nodata is not None and float(nodata).is_integer() or cm != 1.0:
+        assert want.any()
+    y0, y1 = H // 3, H - 5
+    assert np.array_equal(ops.nodata_map(d, spec, y0, y1).cpu().numpy(), want[y0:y1])
+    # the per-window masks of kernel 1 over the non-overlapping window cover, scattered back
+    win = 224 if min(H, W) >= 224 else 64
+    ty, tx = ops.window_origins(H, win, win, True), ops.window_origins(W, win, win, True)
+    wt = torch.tensor([(0, t, l) for t in ty for l in tx], dtype=torch.int32, device=cuda_dev)
+    m = ops.preprocess(d.unsqueeze(0), spec, windows=wt, win=win, want_f32=False, want_mask_px=True)["mask_px"]
+    assert np.array_equal(IU.scatter_window_masks(m, len(ty), len(tx), H, W, win).cpu().numpy(), want)
+
+
+def test_nodata_map_with_fmask(cuda_dev):
+    """Fmask-flagged pixels are replaced by no_data_value before scaling (data_pipeline.py:229-267), per timestep
+    ('each') or for every timestep ('any'): the tile map equals kernel 1's pixel mask of the same pixels."""
+    from instageo_b200 import ops
+    rng = np.random.default_rng(12)
+    T, H, W = 2, 224, 224
+    tile = rng.integers(1, 3000, size=(T * 6, H, W)).astype(np.int16)
+    fm = (rng.random((T, H, W)) < 0.05).astype(np.uint8) * 2      # bit 1 = cloud
+    fm[0, :10, :10] = 8
+    d, dfm = torch.from_numpy(tile).to(cuda_dev), torch.from_numpy(fm).to(cuda_dev)
+    spec = ops.PreprocessSpec(FLOOD_MEAN, FLOOD_STD, T, None, 1.0, -9999, cuda_dev)
+    for strategy in ("each", "any"):
+        for bits in (0b10, 0b1010):
+            got = ops.nodata_map(d, spec, fmask=dfm, fmask_bits=bits, masking_strategy=strategy)
+            ref = ops.preprocess(d.unsqueeze(0), spec, want_f32=False, want_mask_px=True, fmask=dfm.unsqueeze(0),
+                                 fmask_bits=bits, masking_strategy=strategy)["mask_px"][0]
+            assert torch.equal(got, ref) and bool(got.any())
+    # without a nodata value nothing can be flagged, whatever the Fmask says
+    spec0 = ops.PreprocessSpec(FLOOD_MEAN, FLOOD_STD, T, None, 1.0, None, cuda_dev)
+    assert not bool(ops.nodata_map(d, spec0, fmask=dfm, fmask_bits=2).any())
+
+
+def test_tile_engine_host_rows_and_device_tile_agree(cuda_dev):
+    """The engine uploads only the raster rows a rank touches when the tile is a host array; the result equals the
+    device-resident path, for whole tiles, stripes, pinned and pageable sources, and is stable across repeated runs
+    (cached buffers, CUDA-graph replay with new logit slices)."""
+    from instageo_b200.model import PrithviSeg
+    from instageo_b200.model import infer_utils as IU
+    variant, T, nc, depth = "prithvi_eo_tiny", 1, 2, 1
+    sd = P.make_state_dict(variant, T, nc, depth=depth, seed=33, stress=True)
+    m = PrithviSeg(temporal_step=T, num_classes=nc, load_pretrained_weights=False, variant=variant, depth=depth)
+    m.load_state_dict(sd)
+    m.to(cuda_dev).eval()
+    rng = np.random.default_rng(5)
+    H, W = 700, 520
+    tile = rng.integers(0, 10001, size=(6, H, W)).astype(np.int16)
+    tile[:, 300:360, 100:250] = -9999
+    kw = dict(window_size=(224, 224), stride=112, batch_size=7, mean=[v * 1e4 for v in FLOOD_MEAN],
+              std=[v * 1e4 for v in FLOOD_STD], constant_multiplier=1.0, no_data_value=-9999)
+    d_tile = torch.from_numpy(tile).to(cuda_dev)
+    full = IU.sliding_window_inference(d_tile, m, return_tensor=True, **kw)
+    assert bool((full[300:360, 100:250] == -1).all()) and len(torch.unique(full)) == 3
+    pinned = torch.from_numpy(tile).pin_memory()
+    for src in (tile, pinned, d_tile, tile):
+        assert torch.equal(IU.sliding_window_inference(src, m, return_tensor=True, **kw), full)
+    for ws in (3, 5):
+        for r in range(ws):
+            y0, y1 = IU.stripe_rows(H, ws, r)
+            for src in (pinned, d_tile):
+                part = IU.sliding_window_inference(src, m, rows=(y0, y1), return_tensor=True, **kw)
+                assert torch.equal(part, full[y0:y1])
+    # world_size 1 through the sharded entry (in-place gather buffer, no collective)
+    assert torch.equal(IU.sliding_window_inference_sharded(pinned, m, 0, 1, **kw), full)
+
+
 def test_sharded_tile_is_bit_identical_across_gpu_counts():
     """end-to-end tile, 1 vs N GPUs -- needs a multi-GPU box (skipped on one GPU; the same script,
     tools/check_tile_sharded.py, was run by hand at 2 and 8 GPUs: PASS)."""

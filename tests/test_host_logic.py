@@ -136,3 +136,75 @@ def test_exchange_plan_is_consistent(height, stride):
         assert sorted(owned) == list(range(len(ys)))
         if world == 1:
             assert plan[0][3] == {} and plan[0][4] == {}
+
+
+@pytest.mark.parametrize("height,stride", [(3660, 112), (3660, 224), (1000, 112), (224, 224), (700, 160)])
+def test_tile_engine_window_plan(height, stride):
+    """The engine's plan on FLAT window indices: equal output stripes (one all-gather slot each), window shares balanced
+    to one window, and for every world size each rank's needed windows = its local part + disjoint received parts
+    whose sends exist on the peer -- every window computed exactly once."""
+    win = 224
+    ys = ops.window_origins(height, win, stride, True)
+    nx = len(ys)
+    n_win = len(ys) * nx
+    for world in range(1, 9):
+        stripes = IU.even_stripes(height, world)
+        rows = -(-height // world)
+        assert stripes[0][0] == 0 and max(b for _, b in stripes) == height
+        assert all(a == min(height, r * rows) and b - a <= rows for r, (a, b) in enumerate(stripes))
+        assert all(stripes[i][1] == stripes[i + 1][0] for i in range(world - 1))
+        need = [tuple(v * nx for v in IU.windows_for_rows(ys, win, a, b)) if b > a else (0, 0) for a, b in stripes]
+        own = [IU.partition(n_win, world, q) for q in range(world)]
+        sizes = [b - a for a, b in own]
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n_win
+        plan = IU.interval_plan(need, own)
+        for r, (local, sends, recvs) in enumerate(plan):
+            got = set(range(*local)) if local else set()
+            for q, (lo, hi) in recvs.items():
+                units = set(range(lo, hi))
+                assert not (units & got) and plan[q][1][r] == (lo, hi)
+                assert own[q][0] <= lo and hi <= own[q][1]
+                got |= units
+            assert got == set(range(*need[r])), (world, r)
+            for q, rng in sends.items():
+                assert plan[q][2][r] == rng and own[r][0] <= rng[0] and rng[1] <= own[r][1]
+
+
+def _flat_exchange_worker(rank, world, port, height, stride, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    win = 224
+    ys = ops.window_origins(height, win, stride, True)
+    nx = len(ys)
+    n_win = len(ys) * nx
+    full = torch.arange(n_win * 4, dtype=torch.float32).reshape(n_win, 2, 2)       # "logits" of every window
+    stripes = IU.even_stripes(height, world)
+    need = [tuple(v * nx for v in IU.windows_for_rows(ys, win, a, b)) if b > a else (0, 0) for a, b in stripes]
+    own = [IU.partition(n_win, world, r) for r in range(world)]
+    _, sends, recvs = IU.interval_plan(need, own)[rank]
+    u0, u1 = min(need[rank][0], own[rank][0]), max(need[rank][1], own[rank][1])
+    buf = torch.full((u1 - u0, 2, 2), -1.0)
+    buf[own[rank][0] - u0:own[rank][1] - u0] = full[own[rank][0]:own[rank][1]]       # what the model wrote in place
+    for req in IU._exchange(buf, u0, buf, u0, sends, recvs, world):
+        req.wait()
+    n0, n1 = need[rank]
+    q.put((rank, bool(torch.equal(buf[n0 - u0:n1 - u0], full[n0:n1])), len(sends) + len(recvs)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height,stride", [(2, 3660, 224), (3, 1000, 112)])
+def test_flat_window_exchange_gloo(world, height, stride):
+    """in-place exchange on one union buffer (own windows written by the model, needed ones received): every rank ends
+    up with exactly the windows that cover its output stripe"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() + world * 11 + stride) % 90
+    procs = [ctx.Process(target=_flat_exchange_worker, args=(r, world, port, height, stride, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] for r in res), res
+    assert any(r[2] > 0 for r in res)

@@ -18,8 +18,11 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 mean = [0.14245495, 0.13921481, 0.12434631, 0.31420089, 0.20743526, 0.12046503]
 std = [0.04036231, 0.04186983, 0.05267646, 0.0822221, 0.06834774, 0.05294205]
+from bench import stress_init  # noqa: E402  (randomised BatchNorm statistics / biases: the maps hold both classes)
 torch.manual_seed(0)
-model = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_tiny", depth=2).to(dev).eval()
+model = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_tiny", depth=2)
+stress_init(model, seed=3)
+model = model.to(dev).eval()
 ok = True
 for (H, W, stride) in ((1500, 1100, 112), (1030, 900, 224), (3660, 3660, 112)):
     g = torch.Generator().manual_seed(1042)
@@ -31,9 +34,12 @@ for (H, W, stride) in ((1500, 1100, 112), (1030, 900, 224), (3660, 3660, 112)):
     full = IU.sliding_window_inference(d_tile, model, return_tensor=True, **kw)
     a = IU.sliding_window_inference_sharded(d_tile, model, rank, world, **kw)
     b = IU.sliding_window_inference_sharded(d_tile, model, rank, world, halo_recompute=True, **kw)
-    same = torch.equal(a, full) and torch.equal(b, full)
+    c = IU.sliding_window_inference_sharded(tile.pin_memory(), model, rank, world, **kw)   # host tile: partial upload
+    hist = [int((full == k).sum()) for k in (-1, 0, 1)]
+    same = torch.equal(a, full) and torch.equal(b, full) and torch.equal(c, full) and min(hist) > 0
     ok = ok and same
-    print(f"rank {rank}: {H}x{W} stride {stride}: exchange == single {torch.equal(a, full)}, halo == single {torch.equal(b, full)}", flush=True)
+    print(f"rank {rank}: {H}x{W} stride {stride}: exchange == single {torch.equal(a, full)}, halo == single "
+          f"{torch.equal(b, full)}, host tile == single {torch.equal(c, full)}, class_hist (nodata, 0, 1) {hist}", flush=True)
 t = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
