@@ -123,6 +123,18 @@ def stress_init(model, seed: int = 0) -> None:
                 lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.02)
 
 
+def calibrate_head_bias(model, patches) -> None:
+    """Subtract the per-class mean logit of one batch from the final 1x1 convolution's bias.  Synthetic chips are
+    white noise, so a random-init head's logits are a per-class constant plus small per-pixel fluctuations and the
+    argmax is one class almost everywhere; with zero-mean logits the class map follows the pixels and every class
+    appears.  Weights stay random-init (this is initialisation, done once before any timing; the oracle later runs on
+    the model's final state_dict)."""
+    import torch
+    with torch.no_grad():
+        logits = model.forward_patches(patches, want_logits=True)[0]
+        model.segmentation_head[-1].bias.sub_(logits.mean(dim=(0, 2, 3)))
+
+
 def cpu_oracle_logits(sd, raw, heads, t=None, mean=None, std=None):
     """Reference CPU path for a chip batch: normalise/mask -> PrithviSeg fp32 -> logits (torch f32)."""
     import numpy as np
@@ -214,6 +226,11 @@ def tile_setup(dev):
     tile = torch.randint(0, 10001, (6, H, W), generator=g, dtype=torch.int16)
     yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
     tile[:, (yy + xx) < 700] = -9999  # diagonal nodata wedge, like the corner of an HLS tile
+    from instageo_b200 import ops
+    spec = ops.PreprocessSpec([m * 1e4 for m in FLOOD_MEAN], [s * 1e4 for s in FLOOD_STD], 1, None, 1.0, -9999, dev)
+    wins = torch.tensor([(0, 1800 + 224 * i, 1500) for i in range(8)], dtype=torch.int32, device=dev)
+    pre = ops.preprocess(tile[:, :, :].to(dev).unsqueeze(0), spec, windows=wins, win=224, want_f32=False, want_patches=True)
+    calibrate_head_bias(model, pre["patches"])
     return model, tile.pin_memory()
 
 
@@ -578,6 +595,8 @@ def main():
     n_rot = 4  # rotating input batches: 4 x 115.6 MB > 126 MB L2
     raws = [torch.randint(0, 10001, (BATCH, T * 6, 224, 224), generator=g, dtype=torch.int16) for _ in range(n_rot)]
     d_raws = [r.to(dev) for r in raws]
+    cal = torch.randint(0, 10001, (8, T * 6, 224, 224), generator=torch.Generator().manual_seed(999), dtype=torch.int16)
+    calibrate_head_bias(model, ops.preprocess(cal.to(dev), spec, want_f32=False, want_patches=True)["patches"])  # same on every rank
     # N > 1: the step's only collective, one all-gather of the int8 masks [world * 64, 224, 224], runs on a side
     # stream so that it overlaps the next step's compute ("pipelined per macro-batch on a side stream");
     # two result buffers alternate, and the timed region ends only when the last gather has finished.

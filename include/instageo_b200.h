@@ -233,6 +233,24 @@ int ig_chip_mask(const void* chip, int chip_dtype, int n_bands, int64_t height, 
                  unsigned long long* counts, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Raw-tile ingestion and prediction writing, device side.  The reference
+ * reads rasters with rasterio / GDAL (`src.read()`, instageo/model/dataloader.py:672-704) and writes
+ * predictions band by band (instageo/model/infer_utils.py:37-54).  Inflate stays on host threads
+ * (zlib into pinned memory); what GDAL does after it runs here:
+ *
+ * ig_tiff_unpack16: blocks = the inflated TIFF blocks (strips: block_w = W; or tiles) of a 16-bit
+ *   raster, block-major -- block ((plane * nby + by) * nbx + bx) at a fixed stride of
+ *   block_h * block_w * (planar ? 1 : spp) samples, still horizontally differenced (predictor 2) /
+ *   byte-swapped / pixel-interleaved as stored in the file.  Undoes the predictor (wrapping prefix
+ *   sum along x per sample, TIFF 6.0 section 14), swaps bytes, de-interleaves, crops partial edge
+ *   blocks: dst [spp, H, W] uint16 / int16 (same bits) -- the raster ig_preprocess reads in place.
+ * ig_tiff_predict: forward horizontal differencing of `rows` rows of W 1- or 2-byte samples (one band
+ *   plane, e.g. int8 class maps [n * H, W]) ahead of the host's Deflate. */
+int ig_tiff_unpack16(const void* blocks, void* dst, int W, int H, int spp, int block_w, int block_h,
+                     int planar, int predictor, int byteswap, void* stream);
+int ig_tiff_predict(const void* src, void* dst, int sample_bytes, int64_t rows, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Eval-mode streaming metrics accumulated on the device.
  * Replaces the per-step host round trip of
  *   RunningConfusionMatrix.update   instageo/model/metrics.py:86-108
@@ -282,6 +300,9 @@ int ig_regression_update(const float* y_true, const float* y_pred, int64_t n, in
 #define IG_PROF_FAMILIES 7
 int ig_profile_enable(int on);
 int ig_profile_report(double* ms, int* launches, int ncat);
+/* the same records one by one, in launch order: ms[i] / family[i] of the first `cap` launches since the
+ * last report; returns the number of launches recorded (clears them). */
+int ig_profile_report_launches(double* ms, int* family, int cap);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
     "ig_linear": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ig_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ig_attention": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ig_tiff_unpack16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "ig_tiff_predict": (_I, [_P, _P, _I, _I64, _I, _P]),
     "ig_chip_mask": (_I, [_P, _I, _I, _I64, _I64, _P, _I, _U32, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
     "ig_confusion_update": (_I, [_P, _P, _I, _I64, _I, _I, _I64, _P, _P, _P]),
     "ig_seg_metrics_update": (_I, [_P, _I64, _I, _I64, _P, _I, _I, _I64, _P, _P, _I, _F, _F, _P, _P, _P]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "ig_regression_update": (_I, [_P, _P, _I64, _I, _F, _F, _F, _P, _P, _P]),
     "ig_profile_enable": (_I, [_I]),
     "ig_profile_report": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int), _I]),
+    "ig_profile_report_launches": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int), _I]),
 }
 
 _lib = None
@@ -124,6 +127,15 @@ PROF_FAMILIES = ["preprocess", "stitch", "gemm_linear", "gemm_conv", "attention"
 
 def profile_enable(on: bool) -> None:
     check(load().ig_profile_enable(int(on)))
+
+
+def profile_launches(cap: int = 4096) -> list:
+    """[(family, milliseconds)] of every launch since the last report, in launch order."""
+    ms, cat = (C.c_double * cap)(), (C.c_int * cap)()
+    n = load().ig_profile_report_launches(ms, cat, cap)
+    if n < 0:
+        check(n)
+    return [(PROF_FAMILIES[cat[i]], ms[i]) for i in range(min(n, cap))]
 
 
 def profile_report() -> dict:

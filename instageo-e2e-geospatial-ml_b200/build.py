@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libinstageo_b200.so")
 SOURCES = ["ig_runtime.cu", "preprocess.cu", "stitch.cu", "elementwise.cu", "gemm_tc.cu", "attention.cu", "model.cu",
-           "metrics.cu", "chipmask.cu"]
+           "metrics.cu", "chipmask.cu", "tiffio.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

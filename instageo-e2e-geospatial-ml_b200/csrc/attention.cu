@@ -10,10 +10,13 @@
 // with its K / V / Q loads and QK^T issue running two KV blocks ahead, across item boundaries (see the comment on
 // the kernel).  tcgen05 throughout:
 //   S_j  = Q K_j^T  : UMMA 128x64x16, both operands K-major (128-byte swizzle), S double-buffered in TMEM
-//   O   += P_j V_j  : UMMA 128x64x16, A = P_j (bf16, written to swizzled smem by the softmax warps),
+//   O   += P_j V_j  : UMMA 128x64x16, A = P_j read from TENSOR MEMORY (bf16 pairs written by the softmax warps with
+//                     tcgen05.st over the columns of S_j they have just pulled into registers: no shared-memory
+//                     round trip, no fence.proxy.async, and the 32 KB of P buffers per CTA went to deeper K / V rings),
 //                     B = V_j used MN-major straight from its [kv, 64] tile (no transpose pass)
 //   L   += P_j 1    : UMMA 128x8x16 against a tile of ones: the softmax denominator is accumulated by the
-//                     tensor core from the SAME bf16-rounded probabilities as the numerator
+//                     tensor core from the SAME bf16-rounded probabilities as the numerator (summing it in the
+//                     softmax threads' registers instead cost 12 % of the kernel: 64 dependent-on-MUFU adds per block)
 // O and L stay in TMEM for the whole KV loop.  The softmax warps (thread <-> TMEM lane <-> query row)
 // therefore do nothing per block but: pull the 64 scores, take their max, exponentiate against a
 // reference max, and write P_j.  The reference max is LAZY: it is only raised when a block's max exceeds
@@ -31,21 +34,31 @@ namespace attn {
 constexpr int BQ = 128, BKV = 64, HD = 64;
 constexpr int Q_BYTES = BQ * HD * 2;    // 16384
 constexpr int KV_BYTES = BKV * HD * 2;  // 8192
-constexpr int K_STAGES = 4, V_STAGES = 3;
-constexpr int L2_AHEAD = 6;  // KV blocks between a tile's L2 prefetch and its TMA load
+constexpr int K_STAGES = 5, V_STAGES = 6;
 constexpr int OFF_Q = 0;                              // [128 x 64] bf16
 constexpr int OFF_K = OFF_Q + Q_BYTES;
 constexpr int OFF_V = OFF_K + K_STAGES * KV_BYTES;
-constexpr int OFF_P = OFF_V + V_STAGES * KV_BYTES;   // 2 x [128 x 64] bf16 (one swizzle atom column each)
-constexpr int P_BYTES = BQ * BKV * 2;                 // 16384
-constexpr int OFF_ONES = OFF_P + 2 * P_BYTES;         // [8 x 64] bf16 ones (K-major B operand of the L MMA)
+constexpr int OFF_ONES = OFF_V + V_STAGES * KV_BYTES;  // [8 x 64] bf16 ones (K-major B operand of the L MMA)
 constexpr int OFF_BAR = OFF_ONES + 1024;
-constexpr int SMEM_TOTAL = 1024 + OFF_BAR + 256;
+constexpr int SMEM_TOTAL = 1024 + OFF_BAR + 512;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_O = 128, COL_L = 192;  // S buffers at 0 / 64, O at 128..191, L at 192..199
+// TMEM columns (256 = the whole allocation of a CTA, two CTAs per SM): S buffers at 0 / 64 (128 x 64 f32), ONE P
+// buffer at 128 (128 x 64 bf16 = 32 columns of bf16 pairs), O at 160..223, L at 224..231.  P has its OWN columns:
+// with P_j written over S_j the buffer could only be handed back to QK^T_{j+2} after PV_j, and that chain (publish
+// P_j -> PV_j -> free -> QK^T_{j+2} -> S_{j+2}) was longer than the softmax of block j+1 it has to hide under.  One
+// buffer is enough: PV_{j-1}, issued when block j-1 was published, completes long before block j has been
+// exponentiated.
+constexpr int COL_S = 0, COL_P = 128, COL_O = 160, COL_L = 224;
+// ATTN_P_ALIAS = 1: P_j is written over columns [0, 32) of S_j instead (every softmax warp overwrites only the lanes
+// whose scores it holds in registers) and the S buffer returns to QK^T_{j+2} with PV_j's commit.  Measured on B200
+// (64 x 589 x 12 heads, CUDA events, same process): aliased 127-131 us, own P columns 138-142 us -- the shorter
+// softmax stream (no second barrier pair) wins over the shorter dependency chain, so the alias form ships.
+#ifndef ATTN_P_ALIAS
+#define ATTN_P_ALIAS 1
+#endif
 constexpr float RESCALE_LOG2 = 8.f;                 // raise the reference max only for jumps > 2^8
-static_assert(OFF_ONES % 1024 == 0 && OFF_K % 1024 == 0, "UMMA operand tiles are 1024-byte aligned");
+static_assert(OFF_ONES % 1024 == 0 && OFF_V % 1024 == 0 && OFF_K % 1024 == 0, "UMMA operand tiles are 1024-byte aligned");
 static_assert(2 * SMEM_TOTAL <= 232448 - 2048, "two CTAs per SM");
 // Timing ablations (tools/attn_ablate.sh; never defined in the shipped library): 1 = no MUFU (exp2 -> identity),
 // 2 = no P stores, 5 / 6 / 7 = one instead of four L / PV / QK UMMAs per KV block.  Results are wrong by construction.
@@ -79,6 +92,24 @@ __device__ __forceinline__ void attn_trace(int role, int ev, int blk) {
 #define PROF_ADD(slot, t0, t1)
 #define TRACE(role, ev, blk)
 #endif
+#ifndef ATTN_POLY
+#define ATTN_POLY 1
+#endif
+#ifndef ATTN_STALE_MAX
+#define ATTN_STALE_MAX 1
+#endif
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial of 2^f on [-0.5, 0.5], relative error
+// 7.7e-5 -- far below the bf16 rounding of P): round-to-nearest integer part through the 1.5 * 2^23 magic add, whose
+// low mantissa bits are then shifted into the exponent field.  x is clamped to >= -125 (such probabilities round to
+// zero against a row's maximum anyway).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  const float p = fmaf(f, fmaf(f, fmaf(f, 0.05508868396282196f, 0.24260404706001282f), 0.6932762265205383f),
+                       0.9999289512634277f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ float exp2_or_ablate(float x) {
 #if ATTN_ABLATE == 1
   return x;
@@ -104,17 +135,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;    // [1]
   uint64_t* q_empty = bars + 1;   // [1]  every QK^T of the item has completed
-  uint64_t* k_full = bars + 2;    // [4]
-  uint64_t* k_empty = bars + 6;   // [4]
-  uint64_t* v_full = bars + 10;   // [3]
-  uint64_t* v_empty = bars + 13;  // [3]
-  uint64_t* s_full = bars + 16;   // [2]
-  uint64_t* s_free = bars + 18;   // [2]
-  uint64_t* p_full = bars + 20;   // [2]
-  uint64_t* p_free = bars + 22;   // [2]
-  uint64_t* o_done = bars + 24;   // [2]  PV of a block (and everything before it) has completed
-  uint64_t* o_free = bars + 26;   // [1]  the softmax warps have read O / L of the finished item
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* k_full = bars + 2;                  // [K_STAGES]
+  uint64_t* k_empty = k_full + K_STAGES;        // [K_STAGES]
+  uint64_t* v_full = k_empty + K_STAGES;        // [V_STAGES]
+  uint64_t* v_empty = v_full + V_STAGES;        // [V_STAGES]
+  uint64_t* s_full = v_empty + V_STAGES;        // [2]
+  uint64_t* s_free = s_full + 2;                // [2]  the softmax warps hold S_j in registers
+  uint64_t* p_full = s_free + 2;                // [2] (own P columns: only [0], one P buffer)
+  uint64_t* p_free = p_full + 2;                // [2] (own P columns only, [0]): PV_j has consumed P_j
+  uint64_t* o_done = p_free + 2;                // [2]  PV of a block (and everything before it) has completed
+  uint64_t* o_free = o_done + 2;                // [1]  the softmax warps have read O / L of the finished item
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 1);
+  static_assert((2 + 2 * K_STAGES + 2 * V_STAGES + 11) * 8 + 4 <= 512, "barrier block");
 
   const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
   PROF_T(cta0);
@@ -128,7 +160,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     ig::mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       ig::mbar_init(&s_full[s], 1);
-      ig::mbar_init(&s_free[s], 4);
+      ig::mbar_init(&s_free[s], ATTN_P_ALIAS ? 1 : 4);
       ig::mbar_init(&p_full[s], 4);
       ig::mbar_init(&p_free[s], 1);
       ig::mbar_init(&o_done[s], 1);
@@ -157,6 +189,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
   __syncthreads();
   ig::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  ig::pdl_launch_dependents();  // programmatic dependent launch: see ig::launch
+  ig::pdl_wait();
 
   // Both issuing warps need these (uniform values; descriptors are formed ADDITIVELY from base words computed
   // once: start address >> 4 in the low word, a stage / buffer / K-step is a constant added to it, so a UMMA costs
@@ -218,7 +252,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       }
       __syncwarp();
       --k_left;
+#if ATTN_ABLATE != 11
       k_row += BKV;
+#endif
       if (++k_st == K_STAGES) k_st = 0, k_par ^= 1;
       if (++k_j == nb) {
         k_j = 0, k_w += w_step;
@@ -293,7 +329,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     // ===================== warp 1: V loads + PV issuer (whole warp walks the loop, one elected lane issues) =====
     const uint32_t idesc_o = ig::umma_idesc_bf16(BQ, HD, 0, 1);   // O += P V  (B = V, MN-major)
     const uint32_t idesc_l = ig::umma_idesc_bf16(BQ, 8, 0, 0);    // L += P 1  (B = ones, K-major, N = 8)
-    const uint32_t p_lo = ig::umma_desc_lo(smem_base + OFF_P);
     const uint32_t one_lo = ig::umma_desc_lo(smem_base + OFF_ONES);
     // V is consumed MN-major straight from its [kv, 64] tile: 16 kv rows of 128 bytes per K step, 8-row groups
     // 1024 B apart (LBO = SBO = 1024)
@@ -322,7 +357,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       }
       __syncwarp();
       --v_left;
+#if ATTN_ABLATE != 11
       v_row += BKV;
+#endif
       if (++v_st == V_STAGES) v_st = 0, v_par ^= 1;
       if (++v_j == nb) {
         v_j = 0, v_w += w_step;
@@ -345,28 +382,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
 #endif
       TRACE(1, 14, g);  // V ready
       PROF_ADD(12, m1, m1b);  // wait V_g
-      ig::mbar_wait(&p_full[pb], pf_par);  // P_g is in smem and any rescale of O / L is finished
+      // P_g is in tensor memory and any rescale of O / L is finished.  Aliased P: the softmax warps may publish P_{g+1}
+      // (other S buffer) before this warp has seen P_g, so the two buffers have a barrier each.
+      ig::mbar_wait(&p_full[ATTN_P_ALIAS ? pb : 0], pf_par);
       // first block of an item overwrites O / L: the previous item's epilogue must have read them
       if (j == 0 && n > 0) ig::mbar_wait(o_free, (n - 1) & 1);
       PROF_T(m2);
       TRACE(1, 12, g);  // V and P ready
       ig::tc_fence_after();
-      const uint32_t dp = p_lo + pb * (P_BYTES >> 4);
+      const uint32_t tp = ATTN_P_ALIAS ? tmem_base + COL_S + pb * BKV : tmem_base + COL_P;   // P_g: 128 lanes x 32 columns
       const uint32_t dv = v_lo + sv * (KV_BYTES >> 4);
       const uint32_t acc0 = j > 0 ? 1u : 0u;
       if (ig::elect_one()) {
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          // A = P_g: 128 rows x 64 kv (one swizzle atom column), 32 bytes per K step
-          const uint64_t da = ig::umma_desc_pack(dp + 2 * k);
+          // A = P_g from tensor memory: 16 kv (one K step) = 8 columns of bf16 pairs
           if (ATTN_ABLATE != 6 || k == 0)
-            ig::umma_bf16(tmem_base + COL_O, da, ig::umma_desc_pack(dv + k * (2048 >> 4)), idesc_o, k > 0 ? 1u : acc0);
+            ig::umma_bf16_ts(tmem_base + COL_O, tp + 8 * k, ig::umma_desc_pack(dv + k * (2048 >> 4)), idesc_o, k > 0 ? 1u : acc0);
           if (ATTN_ABLATE != 5 || k == 0)
-            ig::umma_bf16(tmem_base + COL_L, da, ig::umma_desc_pack(one_lo + 2 * k), idesc_l, k > 0 ? 1u : acc0);
+            ig::umma_bf16_ts(tmem_base + COL_L, tp + 8 * k, ig::umma_desc_pack(one_lo + 2 * k), idesc_l, k > 0 ? 1u : acc0);
         }
         ig::umma_commit(&o_done[pb]);
         ig::umma_commit(&v_empty[sv]);
-        ig::umma_commit(&p_free[pb]);
+        if (ATTN_P_ALIAS) ig::umma_commit(&s_free[pb]);   // the S / P buffer may be overwritten by QK^T of block g + 2
+        else ig::umma_commit(&p_free[0]);
       }
       __syncwarp();
       PROF_T(m3);
@@ -376,7 +415,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       if (++j == nb) j = 0, ++n;
       if (++sv == V_STAGES) sv = 0, vf_par ^= 1;
       pb ^= 1;
-      if (pb == 0) pf_par ^= 1;
+      if (!ATTN_P_ALIAS || pb == 0) pf_par ^= 1;
       // V_{g+2} goes into the buffer PV_{g-1} released (that commit was issued one iteration ago)
       if (v_left > 0) emit_v();
     }
@@ -385,7 +424,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t t_s = t_lane + COL_S, t_o = t_lane + COL_O, t_l = t_lane + COL_L;
+    const uint32_t t_s = t_lane + COL_S, t_o = t_lane + COL_O, t_p = t_lane + COL_P, t_l = t_lane + COL_L;
     const float sl2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
     const float jump = RESCALE_LOG2 / sl2;           // the same threshold in raw score units
     const uint32_t NEG_INF = 0xff800000u;
@@ -398,6 +437,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
       const int h = bh % heads, b = bh / heads;
       const int row0 = b * N, q0 = qt * BQ;
       float m_ref = -INFINITY;
+      float m_seen = -INFINITY;   // running maximum of the row over the blocks seen so far (ATTN_STALE_MAX)
       for (int j = 0; j < nb; ++j, ++g) {
         const int kv0 = j * BKV, sb = g & 1;
         const uint32_t par = (g >> 1) & 1;
@@ -410,90 +450,127 @@ attention_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant_
         ig::tmem_ld32(t_s + sb * BKV, sa);
         ig::tmem_ld32(t_s + sb * BKV + 32, sb2);
         ig::tmem_ld_wait();
+#if !ATTN_P_ALIAS
         // the scores are in registers: hand the S buffer back so QK^T of block g+2 can start
         ig::tc_fence_before();
         __syncwarp();
         if (lane == 0) ig::mbar_arrive(&s_free[sb]);
+#endif
         PROF_T(c2);
         if (nvalid < BKV) {  // last block: masked columns become -inf (=> exp 0, ignored by the max)
 #pragma unroll
           for (int i = 0; i < 64; ++i)
             if (i >= nvalid) sc[i] = NEG_INF;
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        // block maximum: 8 independent chains of 3-input maxima (4 dependent steps each) and a 3-level tree (the
+        // 4-chain version was bound by the latency of its 8-deep chains: ~220 clk per block in the phase profile)
+        auto block_max = [&]() {
+          float mx[8];
 #pragma unroll
-        for (int i = 0; i < 64; i += 8) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[i + 2]), __uint_as_float(sc[i + 3])));
-          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sc[i + 4]), __uint_as_float(sc[i + 5])));
-          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sc[i + 6]), __uint_as_float(sc[i + 7])));
+          for (int c = 0; c < 8; ++c) mx[c] = fmaxf(__uint_as_float(sc[c]), __uint_as_float(sc[c + 8]));
+#pragma unroll
+          for (int i = 16; i < 64; i += 16)
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(sc[i + c]), __uint_as_float(sc[i + c + 8])));
+          return fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+        };
+        // ---- lazy rescale: O and L of this warp's 32 rows are multiplied by 2^(old - new) in TMEM (rows that keep
+        // their reference by 1).  PV_{g-1} must have completed; PV_g cannot start before this warp arrives on p_full.
+        auto rescale_to = [&](float m_new) {
+          const float alpha = ig::ex2((m_ref - m_new) * sl2);
+          m_ref = m_new;
+          ig::mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          ig::tc_fence_after();
+          uint32_t t[32];
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            ig::tmem_ld32(t_o + c, t);
+            ig::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            ig::tmem_st32(t_o + c, t);
+          }
+          const uint32_t lv = ig::tmem_ld1(t_l);
+          ig::tmem_ld_wait();
+          ig::tmem_st1(t_l, __float_as_uint(__uint_as_float(lv) * alpha));
+          ig::tmem_st_wait();
+        };
+        // ---- exponentials -> P_g (bf16 pairs); fully masked 16-column groups become zeros.  A share of the scores
+        // takes the FMA-pipe polynomial instead of MUFU.EX2 (the MUFU issues one warp instruction per 8 clk and is
+        // shared by the softmax warps of both resident CTAs): ATTN_POLY = 1 one in four, 2 one in two.
+        uint32_t pk[32];
+        auto exps = [&](float mc) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            if (gq * 16 < nvalid) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float a0 = fmaf(__uint_as_float(sc[gq * 16 + 2 * i]), sl2, -mc);
+                const float a1 = fmaf(__uint_as_float(sc[gq * 16 + 2 * i + 1]), sl2, -mc);
+                const float p0 = exp2_or_ablate(a0);
+                const float p1 = (ATTN_POLY == 2 || (ATTN_POLY == 1 && (i & 1))) ? ex2_poly(a1) : exp2_or_ablate(a1);
+                pk[gq * 8 + i] = ig::pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[gq * 8 + i] = 0u;
+            }
+          }
+        };
+#if ATTN_STALE_MAX
+        // The reference maximum of a row trails by one block: block j is exponentiated against the reference the
+        // EARLIER blocks established (raised, with the O / L rescale, when they exceeded it by more than 2^8), so
+        // its own maximum is not on the critical path -- the FMNMX chains overlap the MUFU-bound exponentials.  Any
+        // common reference gives the same softmax; the only constraint is the float exponent range, checked
+        // afterwards: a score more than 2^64 above the reference (never seen) takes the slow exact path.
+        if (j == 0) {
+          m_ref = block_max();   // PV_0 overwrites O / L (accumulate = 0): nothing to rescale
+          m_seen = m_ref;
+        } else {
+          const bool need = m_seen > m_ref + jump;
+          if (__any_sync(0xffffffffu, need)) rescale_to(need ? m_seen : m_ref);
         }
-        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        PROF_T(c3);
+        PROF_T(c4);
+        TRACE(2, 21 + 100 * warp, g);  // exps start
+        exps(m_ref * sl2);
+        if (j > 0) {
+          const float m_blk = block_max();
+          const bool over = m_blk > m_ref + 8.f * jump;
+          if (__any_sync(0xffffffffu, over)) {
+            rescale_to(over ? m_blk : m_ref);
+            exps(m_ref * sl2);
+          }
+          m_seen = fmaxf(m_seen, m_blk);
+        }
+#else
+        const float m_blk = block_max();
         if (j == 0) {
           m_ref = m_blk;  // PV_0 overwrites O / L (accumulate = 0): nothing to rescale
         } else {
           const bool need = m_blk > m_ref + jump;
-          if (__any_sync(0xffffffffu, need)) {
-            // ---- lazy rescale: O and L of this warp's 32 rows are multiplied by 2^(old - new) in TMEM.
-            // PV_{g-1} must have completed; PV_g cannot start before this warp arrives on p_full below.
-            const float m_new = need ? m_blk : m_ref;
-            const float alpha = ig::ex2((m_ref - m_new) * sl2);  // 1 for rows that keep their reference
-            m_ref = m_new;
-            ig::mbar_wait(&o_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
-            ig::tc_fence_after();
-            uint32_t t[32];
-#pragma unroll
-            for (int c = 0; c < HD; c += 32) {
-              ig::tmem_ld32(t_o + c, t);
-              ig::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-              ig::tmem_st32(t_o + c, t);
-            }
-            const uint32_t lv = ig::tmem_ld1(t_l);
-            ig::tmem_ld_wait();
-            ig::tmem_st1(t_l, __float_as_uint(__uint_as_float(lv) * alpha));
-            ig::tmem_st_wait();
-          }
+          if (__any_sync(0xffffffffu, need)) rescale_to(need ? m_blk : m_ref);
         }
-        const float mc = m_ref * sl2;
-        // ---- exponentials -> P_g (bf16, swizzled smem); fully masked 16-column groups are written as zeros
         PROF_T(c3);
-        ig::mbar_wait(&p_free[sb], par ^ 1);
         PROF_T(c4);
-        TRACE(2, 21 + 100 * warp, g);  // P buffer free, exps start
-        uint8_t* prow = smem + OFF_P + sb * P_BYTES + row * 128;
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          uint32_t pk[8];
-          if (gq * 16 < nvalid) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float p0 = exp2_or_ablate(fmaf(__uint_as_float(sc[gq * 16 + 2 * i]), sl2, -mc));
-              const float p1 = exp2_or_ablate(fmaf(__uint_as_float(sc[gq * 16 + 2 * i + 1]), sl2, -mc));
-              pk[i] = ig::pack_bf16(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = 0u;
-          }
+        TRACE(2, 21 + 100 * warp, g);  // exps start
+        exps(m_ref * sl2);
+#endif
 #if ATTN_ABLATE == 2
-          if (pk[0] == 0x12345678u)
+        if (pk[0] == 0x12345678u)
 #endif
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int chunk = gq * 2 + q;  // 16-byte chunk inside the 128-byte row
-            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
-        }
+#if ATTN_P_ALIAS
+        ig::tmem_st32(t_s + sb * BKV, pk);
+#else
+        ig::mbar_wait(&p_free[0], (g & 1) ^ 1);   // PV_{g-1} has consumed the previous tenant of the P buffer
+        ig::tmem_st32(t_p, pk);
+#endif
         PROF_T(c5);
-#if ATTN_ABLATE != 10
-        ig::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the UMMA async proxy
-#endif
-        ig::tc_fence_before();         // orders a rescale's tcgen05.st before the MMA warp's PV_g
+        ig::tmem_st_wait();
+        ig::tc_fence_before();         // orders the P store (and a rescale's tcgen05.st) before the MMA warp's PV_g
         __syncwarp();
-        if (lane == 0) ig::mbar_arrive(&p_full[sb]);
+        if (lane == 0) ig::mbar_arrive(&p_full[ATTN_P_ALIAS ? sb : 0]);
         PROF_T(c6);
         TRACE(2, 22 + 100 * warp, g);  // P_g published (every softmax warp)
         PROF_ADD(0, c0, c1);  // wait S
@@ -596,11 +673,16 @@ int attention_planned(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* out
   const int nqt = (N + attn::BQ - 1) / attn::BQ;
   IG_REQUIRE(static_cast<int64_t>(nqt) * heads * B < (1ll << 31), IG_ESHAPE, "attention: too many work items");
   const int total_items = nqt * heads * B;
-  const int grid = total_items < 2 * ig_num_sms() ? total_items : 2 * ig_num_sms();
+  int grid = total_items < 2 * ig_num_sms() ? total_items : 2 * ig_num_sms();
+  size_t smem = attn::SMEM_TOTAL;
+  if (getenv("IG_ATTN_ONE_CTA")) {  // measurement aid: one CTA per SM (the second is kept out by the shared-memory request)
+    smem = 150 * 1024;
+    grid = total_items < ig_num_sms() ? total_items : ig_num_sms();
+    cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
   ig::ProfScope prof(ig::PROF_ATTENTION, st);
-  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_TOTAL, st>>>(tmq, tmkv, static_cast<__nv_bfloat16*>(out), N, D,
-                                                                      nqt, heads, total_items);
-  IG_CUDA_OK(cudaGetLastError());
+  IG_CUDA_OK(ig::launch(attn::attention_kernel, dim3(grid), dim3(attn::THREADS), smem, st, true, tmq, tmkv,
+                        static_cast<__nv_bfloat16*>(out), N, D, nqt, heads, total_items));
   return IG_OK;
 }
 int attention(const void* qkv, void* out, int B, int N, int heads, cudaStream_t st) {

@@ -24,6 +24,8 @@ struct LnArgs {
 };
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  ig::pdl_launch_dependents();  // programmatic dependent launch: see ig::launch
+  ig::pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.M) return;
@@ -84,8 +86,7 @@ int layernorm(const float* x, const float* gamma, const float* beta, void* out, 
   LnArgs a{x, gamma, beta, static_cast<__nv_bfloat16*>(out), M, D, mode, ntok, T, g, guard};
   const int wpb = 8;
   ig::ProfScope prof(ig::PROF_LAYERNORM, st);
-  layernorm_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
-  IG_CUDA_OK(cudaGetLastError());
+  IG_CUDA_OK(ig::launch(layernorm_kernel, dim3((M + wpb - 1) / wpb), dim3(wpb * 32), 0, st, true, a));
   return IG_OK;
 }
 
@@ -132,6 +133,8 @@ int patchify(const float* x, void* out, int B, int C, int T, int S, cudaStream_t
 
 // x[b*ntok + 0, :] = cls + pos[0, :]
 __global__ void cls_kernel(float* x, const float* cls, const float* pos, int B, int ntok, int D) {
+  ig::pdl_launch_dependents();
+  ig::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
@@ -139,8 +142,7 @@ __global__ void cls_kernel(float* x, const float* cls, const float* pos, int B, 
 }
 int init_cls(float* x, const float* cls, const float* pos, int B, int ntok, int D, cudaStream_t st) {
   ig::ProfScope prof(ig::PROF_MISC, st);
-  cls_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(x, cls, pos, B, ntok, D);
-  IG_CUDA_OK(cudaGetLastError());
+  IG_CUDA_OK(ig::launch(cls_kernel, dim3((B * D + 255) / 256), dim3(256), 0, st, true, x, cls, pos, B, ntok, D));
   return IG_OK;
 }
 
@@ -220,6 +222,33 @@ __global__ void conv_w_kernel(const float* s, __nv_bfloat16* d, int Cin, int Cou
 }
 int repack_conv_weight(const float* s, void* d, int Cin, int Cout, int transposed, int permT, cudaStream_t st) {
   conv_w_kernel<<<1024, 256, 0, st>>>(s, static_cast<__nv_bfloat16*>(d), Cin, Cout, transposed, permT);
+  IG_CUDA_OK(cudaGetLastError());
+  return IG_OK;
+}
+
+// Phase-stacked transposed convolution: output pixel (2y + pa, 2x + pb) = sum over the 2 x 2 input neighbourhood
+// (y + iy, x + ix) of W[ky][kx] with ky = (pa == 0 ? 1 : iy == 0 ? 2 : 0) -- used iff iy <= pa -- and the same along x
+// (SURVEY.md Appendix A.5).  Row (pa*2 + pb)*Cout + co, column (iy*2 + ix)*Cin + ci; unused blocks are zero.
+__global__ void stack_convt_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ d, int Cin, int Cout) {
+  const int64_t n = static_cast<int64_t>(16) * Cin * Cout;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % (4 * Cin));
+    const int row = static_cast<int>(i / (4 * Cin));
+    const int ph = row / Cout, co = row - ph * Cout;
+    const int tp = col / Cin, ci = col - tp * Cin;
+    const int pa = ph >> 1, pb = ph & 1, iy = tp >> 1, ix = tp & 1;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (iy <= pa && ix <= pb) {
+      const int ky = pa == 0 ? 1 : (iy == 0 ? 2 : 0);
+      const int kx = pb == 0 ? 1 : (ix == 0 ? 2 : 0);
+      v = s[static_cast<int64_t>(co) * 9 * Cin + static_cast<int64_t>(ky * 3 + kx) * Cin + ci];
+    }
+    d[i] = v;
+  }
+}
+int stack_convt_weight(const void* src, void* dst, int Cin, int Cout, cudaStream_t st) {
+  stack_convt_kernel<<<256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), Cin, Cout);
   IG_CUDA_OK(cudaGetLastError());
   return IG_OK;
 }

@@ -66,10 +66,12 @@ __device__ __forceinline__ RowInfo make_row(const Args& a, int r, int phase) {
     ri.orow = static_cast<int64_t>(b) * a.ntok + 1 + tok;
     ri.xx = tok;
   } else if (EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) {
+    // two divisions per row per tile, as multiply-shift: the narrow last head stages are bound by the epilogue's
+    // instruction count (ncu: 12 % tensor pipe, 37 % issue slots on the T = 1 final stage), not by the UMMAs
     const int hw = a.Hp * a.Wp;
-    ri.img = r / hw;
+    ri.img = static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(r)) * a.hw_magic) >> 48);
     const int rem = r - ri.img * hw;
-    ri.yy = rem / a.Wp;
+    ri.yy = static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(rem)) * a.wp_magic) >> 48);
     ri.xx = rem - ri.yy * a.Wp;
     ri.interior = ri.valid && ri.yy >= 1 && ri.yy <= a.Hp - 2 && ri.xx >= 1 && ri.xx <= a.Wp - 2;
     if (EPI == EPI_CONV) {
@@ -155,6 +157,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ig::cluster_sync();  // peer barriers are initialised before anyone signals them
   ig::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  // everything above overlapped the tail of the previous kernel of the stream (programmatic dependent launch);
+  // nothing below may run before that kernel has completed and its writes are visible
+  ig::pdl_launch_dependents();
+  ig::pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -269,6 +275,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_ph = 0;
     int tile_par = 0;
+    auto fill_params = [&](int n0) {
+      __syncwarp();
+      for (int idx = lane; idx < PC_COLS; idx += 32) {
+        const int c = (half + 2 * (idx / GCX)) * GCX + (idx % GCX);
+        if (c < a.block_n) {
+          const int cb = (EPI == EPI_CONVT && a.stack_cout) ? (n0 + c) % a.stack_cout : n0 + c;
+          pc0[idx] = a.bias ? __ldg(a.bias + cb) : 0.f;
+          if (HAS_SHIFT) pc1[idx] = __ldg(a.shift + n0 + c);
+        }
+      }
+      __syncwarp();
+    };
+    const bool one_n_tile = a.num_n_tiles == 1;   // the tile's columns never change: fill the parameter cache once
+    if (one_n_tile) fill_params(0);
     for (int tile = pair; tile < total_tiles; tile += npairs) {
       int phase, mt, nt;
       decode_tile(a, tile, phase, mt, nt);
@@ -278,15 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int r = m0 + row_in_tile;
       const RowInfo ri = make_row<EPI>(a, r, phase);
 
-      __syncwarp();
-      for (int idx = lane; idx < PC_COLS; idx += 32) {
-        const int c = (half + 2 * (idx / GCX)) * GCX + (idx % GCX);
-        if (c < a.block_n) {
-          pc0[idx] = a.bias ? __ldg(a.bias + n0 + c) : 0.f;
-          if (HAS_SHIFT) pc1[idx] = __ldg(a.shift + n0 + c);
-        }
-      }
-      __syncwarp();
+      if (!one_n_tile) fill_params(n0);
       // element offset of this thread's output row (+ n0), -1 = row is not stored
       const bool store_row = (EPI == EPI_CONVT) ? ri.interior : ri.valid;
       const long long obase = store_row ? static_cast<long long>(ri.orow) * a.ldo + n0 : -1ll;
@@ -393,6 +405,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // a load -> add -> store chain per row would expose one DRAM latency per iteration.
           const int nchunk = gcols / EPC;
           const int ch = lane & 7;
+          // phase-stacked transposed convolution: this lane's 16-byte chunk (8 channels of ONE output-parity
+          // phase, stack_cout % 8 == 0) goes to output pixel (2y + a, 2x + b), a row of stack_cout channels
+          long long stack_off = 0;
+          if (EPI == EPI_CONVT && a.stack_cout) {
+            const int c = col0 + ch * EPC;
+            const int ph = c / a.stack_cout;
+            const int Wp2 = 2 * (a.Wp - 2) + 2;
+            stack_off = static_cast<long long>((ph >> 1) * Wp2 + (ph & 1)) * a.stack_cout + (c - ph * a.stack_cout) - c;
+          }
           long long offs[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -400,7 +421,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const long long ob = __shfl_sync(0xffffffffu, obase, row);
             const int tok = (EPI == EPI_PATCH) ? __shfl_sync(0xffffffffu, ri.xx, row) : 0;
             const bool ok = ob >= 0 && ch < nchunk;
-            offs[it] = ok ? ob + col0 + ch * EPC : -1ll;
+            offs[it] = ok ? ob + col0 + ch * EPC + stack_off : -1ll;
             if (EPI == EPI_PATCH) {
               extra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (ok)
@@ -438,6 +459,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float logit[NCP];
 #pragma unroll
         for (int k = 0; k < NCP; ++k) logit[k] = 0.f;
+        // classes in groups of four: a 2-class (flood) or 1-channel (regression) head does a quarter of the 1x1
+        // convolution's FMAs and weight loads of the padded NCP = 16 (this loop, not the UMMAs, bounded the T = 1
+        // head: ~5400 clk per 256-pixel tile against ~650 clk of tensor work)
+        const int nc4 = (a.nc + 3) >> 2;
         const int nchunks = a.block_n / 16;
         for (int ch = half; ch < nchunks; ch += 2) {
           uint32_t vr[16];
@@ -457,11 +482,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float4* w4 = reinterpret_cast<const float4*>(w1s + (col + j) * NCP);
 #pragma unroll
               for (int k4 = 0; k4 < NCP / 4; ++k4) {
-                const float4 w = w4[k4];
-                logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
-                logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
-                logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
-                logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
+                if (k4 < nc4) {
+                  const float4 w = w4[k4];
+                  logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
+                  logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
+                  logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
+                  logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
+                }
               }
             }
           }
@@ -475,8 +502,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (half == 1) {
 #pragma unroll
           for (int k4 = 0; k4 < NCP / 4; ++k4)
-            reinterpret_cast<float4*>(ex)[k4] =
-                make_float4(logit[4 * k4], logit[4 * k4 + 1], logit[4 * k4 + 2], logit[4 * k4 + 3]);
+            if (k4 < nc4)
+              reinterpret_cast<float4*>(ex)[k4] =
+                  make_float4(logit[4 * k4], logit[4 * k4 + 1], logit[4 * k4 + 2], logit[4 * k4 + 3]);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
         if (half == 0 && ri.interior) {
@@ -536,8 +564,7 @@ static int launch_epi(const Plan& p, cudaStream_t stream) {
   const int max_pairs = ig_num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
   ig::ProfScope prof((EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) ? ig::PROF_GEMM_CONV : ig::PROF_GEMM_LINEAR, stream);
-  gemm_kernel<EPI><<<2 * pairs, THREADS, SMEM_TOTAL, stream>>>(p.tmA, p.tmB, p.args);
-  IG_CUDA_OK(cudaGetLastError());
+  IG_CUDA_OK(ig::launch(gemm_kernel<EPI>, dim3(2 * pairs), dim3(THREADS), SMEM_TOTAL, stream, true, p.tmA, p.tmB, p.args));
   return IG_OK;
 }
 
@@ -555,7 +582,11 @@ int launch(const Plan& p, cudaStream_t stream) {
     case EPI_RESID: return launch_epi<EPI_RESID>(p, stream);
     case EPI_PATCH: return launch_epi<EPI_PATCH>(p, stream);
     case EPI_CONV: return launch_epi<EPI_CONV>(p, stream);
-    case EPI_CONVT: return launch_epi<EPI_CONVT>(p, stream);
+    case EPI_CONVT:
+      IG_REQUIRE(a.stack_cout == 0 || (a.num_n_tiles == 1 && a.num_phases == 1 && a.stack_cout % 8 == 0 &&
+                                       a.block_n == 4 * a.stack_cout),
+                 IG_ESHAPE, "gemm: phase-stacked transposed convolution needs one N tile of 4 x %d columns", a.stack_cout);
+      return launch_epi<EPI_CONVT>(p, stream);
     case EPI_FINAL:
       IG_REQUIRE(a.num_n_tiles == 1 && a.nc <= NCP, IG_ESHAPE, "gemm: fused head needs one N tile and nc <= %d", NCP);
       return launch_epi<EPI_FINAL>(p, stream);
@@ -570,11 +601,21 @@ void finish_geometry(Args* a) {
   for (int ph = 0; ph < a->num_phases; ++ph)
     for (int t = 0; t < a->taps[ph].n; ++t)
       if (a->taps[ph].g[t].nsub > maxsub) maxsub = a->taps[ph].g[t].nsub;
+  if (a->Hp > 0 && a->Wp > 0) {
+    const unsigned long long one = 1ull << 48;
+    const unsigned long long hw = static_cast<unsigned long long>(a->Hp) * a->Wp;
+    a->hw_magic = (one + hw - 1) / hw;
+    a->wp_magic = (one + a->Wp - 1) / a->Wp;
+  }
   a->a_bytes = (a->a_box_rows * BK * 2 + 1023) / 1024 * 1024;
   a->b_tap_bytes = ((a->block_n / 2) * BK * 2 + 1023) / 1024 * 1024;
   a->stage_bytes = a->a_bytes + maxsub * a->b_tap_bytes;
   a->num_stages = SMEM_MAIN / a->stage_bytes;
   if (a->num_stages > MAX_STAGES) a->num_stages = MAX_STAGES;
+  if (const char* e = getenv("IG_GEMM_STAGES")) {  // measurement aid: cap the operand ring depth
+    const int cap = atoi(e);
+    if (cap >= 2 && cap < a->num_stages) a->num_stages = cap;
+  }
 }
 
 int pick_block_n(int N) {

@@ -37,6 +37,8 @@ int ig_check_device();  // IG_OK if current device is sm_100, else IG_EARCH (+me
   } while (0)
 
 int ig_num_sms();
+// Programmatic dependent launch of the forward's kernel chain (on unless IG_NO_PDL=1): see ig::launch below.
+bool ig_pdl_enabled();
 
 // cudaFuncSetAttribute is a PER-DEVICE setting: a process that drives several GPUs (one model per device, or the
 // test suite's cuda:1 cases) must configure every kernel once on each of them.  get() = the largest setting made so
@@ -76,6 +78,32 @@ struct ProfScope {
 // ----------------------------------------------------------------------------- device PTX
 #ifdef __CUDACC__
 namespace ig {
+
+// Launch with (optionally) programmatic stream serialisation: the kernel may become resident and run its prologue
+// (shared-memory carve-up, mbarrier init, TMEM allocation, tensor-map prefetch) while its predecessor in the stream is
+// still draining; it must execute pdl_wait() before it touches global memory.  Every kernel of the forward chain calls
+// pdl_launch_dependents() + pdl_wait() right after its prologue (both are no-ops for a plain launch).  The dependents
+// are released once ALL CTAs of the primary have issued the trigger (or exited), i.e. during its last wave, so they
+// can never take SM resources from CTAs of the primary that have not started.  Captured into the forward's CUDA graph
+// these launches become programmatic dependency edges.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool on = pdl && ig_pdl_enabled();
+  cfg.attrs = on ? at : nullptr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -270,6 +298,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with the A operand in TENSOR MEMORY (M = 128 rows on the lanes, K along the columns, two bf16 per 32-bit
+// column: 16 K elements = 8 columns): D[128 x N] += A_tmem[128 x 16] * B_smem[N x 16]^T.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // All previously issued tcgen05.mma of this thread arrive on `bar` when complete

@@ -57,8 +57,12 @@ struct Args {
   int tok_per_img, ntok;  // EPI_PATCH
   const float* pos;
   int Hp, Wp;             // padded input geometry of conv modes (H+2, W+2)
+  unsigned long long hw_magic, wp_magic;  // ceil(2^48 / (Hp*Wp)), ceil(2^48 / Wp): exact division of a row index by
+                                          // multiply-shift (n * d < 2^48), set by finish_geometry
   int out_guard;          // guard rows in front of the output buffer
   int phase_a[4], phase_b[4];  // EPI_CONVT output parity of each phase
+  int stack_cout;         // EPI_CONVT, phase-stacked form (> 0): N = 4 * stack_cout, column block ph = (a, b) of a row is the
+                          // output pixel (2y + a, 2x + b); one phase, one N tile (see plan_conv)
   const float* w1;        // EPI_FINAL: [N][NCP] f32 (class fastest), b1 [NCP]
   const float* b1;
   int nc;

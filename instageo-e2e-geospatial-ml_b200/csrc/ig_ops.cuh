@@ -10,6 +10,8 @@ int init_cls(float* x, const float* cls, const float* pos, int B, int ntok, int 
 int zero_ring(void* buf, int B, int Hp, int Wp, int C, cudaStream_t st);
 int cvt_bf16(const float* s, void* d, int64_t n, cudaStream_t st);
 int repack_conv_weight(const float* s, void* d, int Cin, int Cout, int transposed, int permT, cudaStream_t st);
+// phase-stacked ConvTranspose2d(k3, s2, p1, op1) weights: src = repacked [Cout][9*Cin] (tap-major), dst [4*Cout][4*Cin]
+int stack_convt_weight(const void* src, void* dst, int Cin, int Cout, cudaStream_t st);
 int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* cbias,
             float* scale, float* shift, int C, cudaStream_t st);
 int repack_head1x1(const float* w, const float* b, float* wd, float* bd, int nc, int C, int ncp, cudaStream_t st);

@@ -1,5 +1,6 @@
 // Host runtime glue: thread-local error string, device gate, TMA descriptor encoding.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -47,6 +48,15 @@ int ig_num_sms() {
     dev_cached = dev;
   }
   return sms;
+}
+
+bool ig_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IG_NO_PDL");
+    v = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int IgPerDevice::get() const {
@@ -166,6 +176,26 @@ extern "C" int ig_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on != 0;
   return IG_OK;
+}
+
+// Per-launch form of the report (in launch order): ms[i], cat[i] for the first `cap` launches since the last report;
+// returns the number of launches recorded (may exceed cap) and clears the records.
+extern "C" int ig_profile_report_launches(double* ms, int* cat, int cap) {
+  IG_REQUIRE(ms && cat && cap >= 0, IG_EINVAL, "ig_profile_report_launches: null pointer");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && n < cap) {
+      ms[n] = t;
+      cat[n] = r.cat;
+    }
+    ++n;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return n;
 }
 
 // ms[c] = summed device time of family c since the last report, launches[c] = launch count.

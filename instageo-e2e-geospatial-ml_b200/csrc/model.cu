@@ -33,6 +33,7 @@ struct LayerW {
 };
 struct StageW {
   bf16 *ct_w, *cv_w;
+  bf16* ct_ws;  // phase-stacked transposed-convolution weights [4*Cout][4*Cin], or null (wide stages)
   float *ct_b, *cv_b, *bn_g, *bn_b, *bn_m, *bn_v, *scale, *shift;
 };
 
@@ -235,6 +236,13 @@ extern "C" int ig_model_create(const ig_model_cfg* cfg, ig_model** out) {
     StageW& s = m->st[i];
     const size_t ci = m->dims[i], co = m->dims[i + 1];
     A(s.ct_w, 9 * ci * co); A(s.cv_w, 9 * co * co);
+    // Narrow last stages (Cout <= 64, i.e. the T = 1 flood head's 96 -> 48): the four output-parity phases are
+    // stacked along N (one GEMM, N = 4*Cout over the 2 x 2 input neighbourhood, 7 of 16 weight blocks zero) instead
+    // of four GEMMs of N = Cout.  Tiles of 256 x 48 with one to four K = 96 taps carried 144-576 clk of tensor
+    // work against ~3900 clk of per-tile epilogue: 165 TFLOP/s (ncu launch list, profiles/r02_launches_tile224.csv).
+    s.ct_ws = nullptr;
+    if (4 * co <= static_cast<size_t>(gemm::MAX_BN) && co % 8 == 0 && getenv("IG_NO_CONVT_STACK") == nullptr)
+      A(s.ct_ws, 16 * ci * co);
     A(s.ct_b, co); A(s.cv_b, co); A(s.bn_g, co); A(s.bn_b, co); A(s.bn_m, co); A(s.bn_v, co);
     A(s.scale, co); A(s.shift, co);
   }
@@ -373,6 +381,7 @@ extern "C" int ig_model_finalize(ig_model* m, void* stream) {
   for (int i = 0; i < 4; ++i) {
     StageW& s = m->st[i];
     IG_TRY(ops::bn_fold(s.bn_g, s.bn_b, s.bn_m, s.bn_v, s.cv_b, s.scale, s.shift, m->dims[i + 1], st));
+    if (s.ct_ws) IG_TRY(ops::stack_convt_weight(s.ct_w, s.ct_ws, m->dims[i], m->dims[i + 1], st));
   }
   IG_TRY(ops::repack_head1x1(m->w1_raw, m->b1_raw, m->w1, m->b1, m->nc, m->dims[4], gemm::NCP, st));
   m->finalized = true;
@@ -394,15 +403,15 @@ extern "C" int ig_model_launches_per_forward(const ig_model* m) {
 namespace {
 
 int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in, const void* w, int Cin, int Cout,
-              int B, bool transposed) {
+              int B, bool transposed, bool stacked = false) {
   gemm::Args& a = p->args;
   a = gemm::Args{};
   a.M = B * in.Hp * in.Wp;
-  a.N = Cout;
-  a.block_n = gemm::pick_block_n(Cout);
+  a.N = stacked ? 4 * Cout : Cout;
+  a.block_n = gemm::pick_block_n(a.N);
   a.kc = Cin;
   a.num_m_tiles = (a.M + gemm::PAIR_M - 1) / gemm::PAIR_M;
-  a.num_n_tiles = Cout / a.block_n;
+  a.num_n_tiles = a.N / a.block_n;
   a.a_row_base = in.guard;
   a.Hp = in.Hp;
   a.Wp = in.Wp;
@@ -419,6 +428,22 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
       for (int kx = 0; kx < 3; ++kx) {
         g.shift[kx] = kx;
         g.b_off[kx] = (ky * 3 + kx) * Cin;
+      }
+    }
+  } else if (stacked) {
+    // all four output parities in one accumulator row: N = 4*Cout, B = the stacked weights [4*Cout][4*Cin] whose
+    // column block (iy*2 + ix) multiplies input pixel (y + iy, x + ix); one A tile per iy, shared by ix = 0, 1
+    a.num_phases = 1;
+    a.stack_cout = Cout;
+    a.phase_a[0] = a.phase_b[0] = 0;
+    a.taps[0].n = 2;
+    for (int iy = 0; iy < 2; ++iy) {
+      gemm::TapGroup& g = a.taps[0].g[iy];
+      g.a_off = iy * in.Wp;
+      g.nsub = 2;
+      for (int ix = 0; ix < 2; ++ix) {
+        g.shift[ix] = ix;
+        g.b_off[ix] = (iy * 2 + ix) * Cin;
       }
     }
   } else {
@@ -448,8 +473,8 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
   gemm::finish_geometry(&a);
   p->epi = epi;
   IG_TRY(ig_make_tmap_bf16(&p->tmA, ws + in.off, in.rows, Cin, Cin, a.a_box_rows, gemm::BK));
-  IG_TRY(ig_make_tmap_bf16(&p->tmB, w, Cout, 9 * static_cast<uint64_t>(Cin), 9 * static_cast<uint64_t>(Cin),
-                           a.block_n / 2, gemm::BK));
+  const uint64_t wk = (stacked ? 4 : 9) * static_cast<uint64_t>(Cin);
+  IG_TRY(ig_make_tmap_bf16(&p->tmB, w, a.N, wk, wk, a.block_n / 2, gemm::BK));
   (void)m;
   return IG_OK;
 }
@@ -564,7 +589,8 @@ int build_plan(ig_model* m, int batch, char* ws, ig_fwd_plan** out) {
   for (int i = 0; i < 4 && rc == IG_OK; ++i) {
     const StageW& s = m->st[i];
     const Buf& tb = l.t[i];
-    PLAN_TRY(plan_conv(&fp->convt[i], gemm::EPI_CONVT, m, ws, *in, s.ct_w, m->dims[i], m->dims[i + 1], B, true));
+    PLAN_TRY(plan_conv(&fp->convt[i], gemm::EPI_CONVT, m, ws, *in, s.ct_ws ? s.ct_ws : s.ct_w, m->dims[i],
+                       m->dims[i + 1], B, true, s.ct_ws != nullptr));
     fp->convt[i].args.bias = s.ct_b;
     fp->convt[i].args.out = ws + tb.off;
     fp->convt[i].args.out_guard = tb.guard;
@@ -779,14 +805,16 @@ int capture_graph(ig_model* m, ig_fwd_plan& fp, const FwdIO& io, unsigned flags,
       if (e != cudaSuccess) break;
       if (ty != cudaGraphNodeTypeKernel) { e = cudaErrorUnknown; break; }
       chain.push_back(cur);
+      // _v2: the edges of programmatic dependent launches carry edge data (the plain query refuses them)
       size_t nd = 0;
-      e = cudaGraphNodeGetDependentNodes(cur, nullptr, &nd);
+      e = cudaGraphNodeGetDependentNodes_v2(cur, nullptr, nullptr, &nd);
       if (e != cudaSuccess) break;
       if (nd == 0) break;
       if (nd != 1) { e = cudaErrorUnknown; break; }
       cudaGraphNode_t nxt = nullptr;
+      cudaGraphEdgeData ed;
       size_t one = 1;
-      e = cudaGraphNodeGetDependentNodes(cur, &nxt, &one);
+      e = cudaGraphNodeGetDependentNodes_v2(cur, &nxt, &ed, &one);
       cur = nxt;
     }
   }

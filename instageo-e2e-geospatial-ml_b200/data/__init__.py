@@ -2,4 +2,4 @@
 from .data_pipeline import (  # noqa: F401
     MASK_DECODING_POS, apply_mask, create_chip, decode_fmask_value, mask_segmentation_map,
 )
-from .geotiff import read_geotiff, write_geotiff  # noqa: F401
+from .geotiff import read_geotiff, read_geotiff_device, write_geotiff, write_geotiffs_device  # noqa: F401

@@ -15,9 +15,14 @@ GeoTIFF 1.1 tags that matter for HLS / Sentinel-2 chips and COG tiles:
   with the profile of its source chip has the same georeferencing.
 
 ``read_geotiff`` returns ``(array [bands, H, W], profile)``; ``write_geotiff`` writes a little-endian classic TIFF
-with one strip per band and block of rows (planar), optional Deflate and predictor 2.  Everything here is host code:
-decompression is zlib's, not a GPU kernel -- the device side of this row (predictor undo + de-interleave in front of
-kernel 1) is not built yet.  Pinned by tests/test_geotiff.py against Pillow (libtiff) and OpenCV.
+with one strip per band and block of rows (planar), optional Deflate and predictor 2: host code, pinned by
+tests/test_geotiff.py against Pillow (libtiff) and OpenCV.
+
+Device side (16-bit rasters, the HLS / Sentinel-2 case): ``read_geotiff_device`` inflates the blocks on host threads
+(zlib releases the GIL) straight into one pinned buffer, ships it once, and ``ig_tiff_unpack16`` (csrc/tiffio.cu) undoes
+the predictor, swaps bytes, de-interleaves and crops on the GPU, leaving the planar raster kernel 1 reads in place;
+``write_geotiffs_device`` differences a batch of class maps on the GPU (``ig_tiff_predict``) and deflates the strips on
+host threads.  ``read_geotiff`` is the oracle of both (tests/test_gpu_tiffio.py).
 """
 from __future__ import annotations
 
@@ -147,6 +152,158 @@ def _undo_predictor(block: np.ndarray) -> None:
     np.cumsum(block, axis=1, dtype=block.dtype, out=block)
 
 
+class _Layout:
+    """Block geometry of the first image of a TIFF (what both readers need after the IFD is parsed)."""
+
+    def __init__(self, buf: bytes):
+        self.ifd = ifd = _Ifd(buf)
+        self.W, self.H = ifd.one(256), ifd.one(257)
+        self.spp = ifd.one(277, 1)
+        bits = ifd.get(258, (8,))
+        fmt = ifd.get(339, (1,))
+        if len(set(bits)) != 1 or len(set(fmt)) != 1 or bits[0] not in (8, 16, 32, 64) or fmt[0] not in _SAMPLE_KIND:
+            raise TiffError(f"unsupported sample layout bits={bits} format={fmt}")
+        self.dtype = np.dtype(f"{ifd.e}{_SAMPLE_KIND[fmt[0]]}{bits[0] // 8}")
+        self.compression, self.predictor, self.planar = ifd.one(259, 1), ifd.one(317, 1), ifd.one(284, 1)
+        if self.predictor not in (1, 2):
+            raise TiffError(f"unsupported TIFF predictor {self.predictor}")
+        if self.dtype.kind == "f" and self.predictor == 2:
+            raise TiffError("predictor 2 on floating-point samples is not defined")
+        self.tiled = 322 in ifd.tags
+        if self.tiled:
+            self.bw, self.bh = ifd.one(322), ifd.one(323)
+            self.offsets, self.counts = ifd.get(324), ifd.get(325)
+        else:
+            self.bw, self.bh = self.W, min(ifd.one(278, self.H), self.H)
+            self.offsets, self.counts = ifd.get(273), ifd.get(279)
+        self.nbx, self.nby = -(-self.W // self.bw), -(-self.H // self.bh)
+        self.planes = self.spp if self.planar == 2 else 1
+        self.chunk_spp = 1 if self.planar == 2 else self.spp
+        if len(self.offsets) != self.nbx * self.nby * self.planes:
+            raise TiffError("block count does not match the image geometry")
+
+    def profile(self, dtype_name: str) -> dict:
+        ifd = self.ifd
+        profile = {"width": self.W, "height": self.H, "count": self.spp, "dtype": dtype_name,
+                   "geo_tags": {t: ifd.tags[t] for t in _GEO_TAGS if t in ifd.tags}}
+        scale, tie = ifd.get(33550), ifd.get(33922)
+        if scale and tie and len(tie) >= 6:
+            # affine (a, b, c, d, e, f): x = a*col + b*row + c, y = d*col + e*row + f  (rasterio's Affine order)
+            profile["transform"] = (scale[0], 0.0, tie[3] - tie[0] * scale[0], 0.0, -scale[1], tie[4] + tie[1] * scale[1])
+        keys = ifd.get(34735)
+        if keys and len(keys) >= 4:
+            # ProjectedCSType (3072) wins over GeographicType (2048): files of older GDAL versions carry both for a
+            # projected CRS (2048 = the datum's geographic CRS, e.g. 4326 next to 3072 = 326xx of a UTM HLS chip)
+            found = {}
+            for k in range(keys[3]):
+                kid, loc, _cnt, val = keys[4 + 4 * k: 8 + 4 * k]
+                if kid in (3072, 2048) and loc == 0 and val not in (0, 32767):
+                    found[kid] = val
+            if 3072 in found:
+                profile["crs_epsg"] = found[3072]
+            elif 2048 in found:
+                profile["crs_epsg"] = found[2048]
+        nod = ifd.get(42113)
+        if nod:
+            try:
+                profile["nodata"] = float(nod)
+            except ValueError:
+                pass
+        return profile
+
+
+_PINNED: dict = {}
+
+
+def read_geotiff_device(path: str, device="cuda", threads: int = 8):
+    """-> (CUDA tensor [bands, H, W] int16 | uint16, profile): the device form of ``rasterio.open(path).read()``
+    (instageo/model/dataloader.py:672-704) for 16-bit rasters.  Host: file read, IFD parse, zlib inflate of the blocks
+    on ``threads`` threads into ONE pinned buffer (block-major, still differenced / byte-swapped / interleaved as in
+    the file).  Device: a single H2D copy and ``ig_tiff_unpack16``.  Other sample types raise ``TiffError`` (use
+    ``read_geotiff``): there is no silent host path behind this entry."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .. import _lib
+    with open(path, "rb") as fh:
+        buf = fh.read()
+    lay = _Layout(buf)
+    if lay.dtype.itemsize != 2 or lay.dtype.kind not in "ui":
+        raise TiffError(f"read_geotiff_device handles 16-bit integer rasters; this file holds {lay.dtype.name} "
+                        "(decode it with read_geotiff)")
+    if lay.chunk_spp > 8:
+        raise TiffError(f"{lay.chunk_spp} pixel-interleaved samples: the device kernel takes at most 8 (planar files are unlimited)")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("read_geotiff_device needs a CUDA device: there is no CPU path (use read_geotiff)")
+    block_bytes = lay.bh * lay.bw * lay.chunk_spp * 2
+    n_blocks = len(lay.offsets)
+    key = (n_blocks * block_bytes, dev.index)
+    pinned = _PINNED.get(key)
+    if pinned is None:
+        if len(_PINNED) >= 4:
+            _PINNED.pop(next(iter(_PINNED)))
+        pinned = _PINNED[key] = torch.empty(n_blocks * block_bytes, dtype=torch.uint8).pin_memory()
+    host = pinned.numpy()
+
+    def inflate(i):
+        by = (i // lay.nbx) % lay.nby
+        rows = lay.bh if lay.tiled else min(lay.bh, lay.H - by * lay.bh)
+        expected = rows * lay.bw * lay.chunk_spp * 2
+        raw = _decompress(buf[lay.offsets[i]: lay.offsets[i] + lay.counts[i]], lay.compression, expected)
+        if len(raw) < expected:
+            raise TiffError("truncated TIFF block")
+        host[i * block_bytes: i * block_bytes + expected] = np.frombuffer(raw, dtype=np.uint8, count=expected)
+
+    if n_blocks > 1 and threads > 1:
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(inflate, range(n_blocks)))
+    else:
+        for i in range(n_blocks):
+            inflate(i)
+    tdtype = torch.int16 if lay.dtype.kind == "i" else torch.uint16
+    with torch.cuda.device(dev):
+        d_blocks = pinned.to(dev, non_blocking=True)
+        out = torch.empty((lay.spp, lay.H, lay.W), dtype=torch.int16, device=dev)
+        _lib.call("ig_tiff_unpack16", dev, d_blocks.data_ptr(), out.data_ptr(), lay.W, lay.H, lay.spp, lay.bw, lay.bh,
+                  int(lay.planar == 2), lay.predictor, int(lay.dtype.byteorder == ">"))
+        # the pinned buffer is reused by the next read: its H2D copy must have left the host before we return
+        torch.cuda.current_stream(dev).synchronize()
+    return (out if tdtype == torch.int16 else out.view(torch.uint16)), lay.profile(lay.dtype.newbyteorder("=").name)
+
+
+def write_geotiffs_device(paths, maps, profiles=None, compress: Optional[str] = "deflate", predictor: int = 2,
+                          rows_per_strip: int = 256, threads: int = 8) -> None:
+    """Batched writer of single-band predictions (instageo/model/infer_utils.py:37-54 for a whole batch): ``maps`` CUDA
+    tensor [n, H, W] int8 | uint8 | int16 | uint16.  The horizontal differencing of predictor 2 runs on the GPU over
+    the whole batch (``ig_tiff_predict``), one D2H copy brings the bytes back, the strips are deflated on ``threads``
+    host threads and each map is written with its own profile (georeferencing of its source chip)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .. import _lib
+    if not maps.is_cuda or maps.dim() != 3:
+        raise RuntimeError("write_geotiffs_device needs a CUDA tensor [n, H, W]: there is no CPU path (use write_geotiff)")
+    if maps.dtype not in (torch.int8, torch.uint8, torch.int16, torch.uint16):
+        raise TypeError(f"unsupported dtype {maps.dtype}")
+    n, H, W = maps.shape
+    if len(paths) != n or (profiles is not None and len(profiles) != n):
+        raise ValueError("one path (and profile) per map")
+    maps = maps.contiguous()
+    src = maps
+    if predictor == 2:
+        src = torch.empty_like(maps)
+        _lib.call("ig_tiff_predict", maps.device, maps.data_ptr(), src.data_ptr(), maps.element_size(), n * H, W)
+    host = src.cpu().numpy()
+
+    def one(i):
+        _write_single_band(paths[i], host[i], (profiles[i] if profiles is not None else None), compress, predictor,
+                           rows_per_strip, differenced=predictor == 2)
+
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as pool:
+        list(pool.map(one, range(n)))
+
+
 def read_geotiff(path: str):
     """-> (array [bands, H, W] in the file's sample type, profile dict)."""
     with open(path, "rb") as fh:
@@ -205,11 +362,17 @@ def read_geotiff(path: str):
         profile["transform"] = (scale[0], 0.0, tie[3] - tie[0] * scale[0], 0.0, -scale[1], tie[4] + tie[1] * scale[1])
     keys = ifd.get(34735)
     if keys and len(keys) >= 4:
+        # ProjectedCSType (3072) wins over GeographicType (2048): files written by older GDAL versions carry both for
+        # a projected CRS (2048 = the datum's geographic CRS, e.g. 4326, next to 3072 = 326xx of a UTM HLS chip)
+        found = {}
         for k in range(keys[3]):
             kid, loc, _cnt, val = keys[4 + 4 * k: 8 + 4 * k]
-            if kid in (3072, 2048) and loc == 0 and val not in (0, 32767):   # ProjectedCSType / GeographicType
-                profile["crs_epsg"] = val
-                break
+            if kid in (3072, 2048) and loc == 0 and val not in (0, 32767):
+                found[kid] = val
+        if 3072 in found:
+            profile["crs_epsg"] = found[3072]
+        elif 2048 in found:
+            profile["crs_epsg"] = found[2048]
     nod = ifd.get(42113)
     if nod:
         try:
@@ -219,8 +382,14 @@ def read_geotiff(path: str):
     return out, profile
 
 
+def _write_single_band(path, plane: np.ndarray, profile, compress, predictor, rows_per_strip, differenced: bool) -> None:
+    """write_geotiff for one [H, W] plane whose rows are ALREADY horizontally differenced (device writer)."""
+    write_geotiff(path, plane, profile, compress=compress, predictor=predictor, rows_per_strip=rows_per_strip,
+                  _differenced=differenced)
+
+
 def write_geotiff(path: str, array: np.ndarray, profile: Optional[dict] = None, compress: Optional[str] = "deflate",
-                  predictor: int = 1, rows_per_strip: int = 256) -> None:
+                  predictor: int = 1, rows_per_strip: int = 256, _differenced: bool = False) -> None:
     """array [bands, H, W] or [H, W] -> little-endian classic TIFF, planar strips.  ``profile["geo_tags"]`` (as
     returned by ``read_geotiff``) is copied, so a prediction inherits the georeferencing of its source chip."""
     a = np.asarray(array)
@@ -241,7 +410,7 @@ def write_geotiff(path: str, array: np.ndarray, profile: Optional[dict] = None, 
     for b in range(bands):
         for y0 in range(0, H, rows_per_strip):
             blk = np.ascontiguousarray(le[b, y0:y0 + rows_per_strip])
-            if predictor == 2:
+            if predictor == 2 and not _differenced:
                 d = blk.copy()
                 d[:, 1:] = blk[:, 1:] - blk[:, :-1]       # wraps for integer types, as the decoder expects
                 blk = d

@@ -131,13 +131,23 @@ def process_raw_chips(raw, mean: Sequence[float], std: Sequence[float], temporal
 
 
 def get_raster_data(fname, is_label: bool = True, bands: Optional[List[int]] = None,
-                    no_data_value: Optional[int] = -9999, mask_cloud: bool = True, water_mask: bool = False) -> np.ndarray:
+                    no_data_value: Optional[int] = -9999, mask_cloud: bool = True, water_mask: bool = False,
+                    device=None):
     """instageo/model/dataloader.py:672-704 for a single GeoTIFF: ``rasterio.open(fname).read()`` (all bands,
     [bands, H, W], file dtype) and the band gather for non-label rasters.  rasterio when importable, else the
     in-repo TIFF codec (``instageo_b200.data.geotiff``: strips / tiles, none / Deflate / LZW, predictor 2).  The
-    multi-file dict form of the reference (``open_mf_tiff_dataset``, xarray) is out of scope."""
+    multi-file dict form of the reference (``open_mf_tiff_dataset``, xarray) is out of scope.
+
+    ``device``: return a CUDA tensor instead -- 16-bit rasters are inflated on host threads into pinned memory and
+    unpacked (predictor, byte order, de-interleave) by ``ig_tiff_unpack16`` on the GPU, ready for kernel 1."""
     if isinstance(fname, dict):
         raise NotImplementedError("multi-file tile dictionaries (open_mf_tiff_dataset / xarray) are out of scope")
+    if device is not None:
+        from ..data.geotiff import read_geotiff_device
+        data = read_geotiff_device(fname, device)[0]
+        if (not is_label) and bands:
+            data = data[list(bands)]
+        return data
     try:
         import rasterio  # type: ignore
         with rasterio.open(fname) as src:
