@@ -18,11 +18,15 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 mean = [0.14245495, 0.13921481, 0.12434631, 0.31420089, 0.20743526, 0.12046503]
 std = [0.04036231, 0.04186983, 0.05267646, 0.0822221, 0.06834774, 0.05294205]
-from bench import stress_init  # noqa: E402  (randomised BatchNorm statistics / biases: the maps hold both classes)
+from bench import calibrate_head_bias, stress_init  # noqa: E402  (randomised BatchNorm statistics, zero-mean logits)
+from instageo_b200 import ops  # noqa: E402
 torch.manual_seed(0)
 model = PrithviSeg(temporal_step=1, num_classes=2, load_pretrained_weights=False, variant="prithvi_eo_tiny", depth=2)
 stress_init(model, seed=3)
 model = model.to(dev).eval()
+cal = torch.randint(0, 10001, (8, 6, 224, 224), generator=torch.Generator().manual_seed(999), dtype=torch.int16).to(dev)
+spec = ops.PreprocessSpec([m * 1e4 for m in mean], [s * 1e4 for s in std], 1, None, 1.0, -9999, dev)
+calibrate_head_bias(model, ops.preprocess(cal, spec, want_f32=False, want_patches=True)["patches"])  # both classes appear
 ok = True
 for (H, W, stride) in ((1500, 1100, 112), (1030, 900, 224), (3660, 3660, 112)):
     g = torch.Generator().manual_seed(1042)
