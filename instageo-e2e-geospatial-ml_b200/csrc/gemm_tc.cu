@@ -106,6 +106,48 @@ __device__ __forceinline__ uint4* stg_slot(uint8_t* stg, int row, int chunk) {
   return reinterpret_cast<uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// EPI_FINAL inner math for one 16-channel accumulator chunk of a pixel: BatchNorm(eval) + ReLU, then the 1x1 class
+// convolution as f32 FMAs, classes in groups of four.  NC4 (= ceil(nc / 4)) is a COMPILE-TIME count: with a run-time
+// bound inside the unrolled loop ptxas predicated the FMAs off instead of skipping them, and a 2-class head still
+// issued all 16 per channel (ncu source page: 38 % of the T = 1 final stage's 990 M warp instructions were FFMA).
+template <int NC4>
+__device__ __forceinline__ void final_chunk(const uint32_t (&vr)[16], const float* pc0, const float* pc1, const float* w1row,
+                                            float (&logit)[NCP]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 sc = *reinterpret_cast<const float4*>(pc0 + 4 * j4);
+    const float4 sh = *reinterpret_cast<const float4*>(pc1 + 4 * j4);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * j4 + jj;
+      const float act = fmaxf(fmaf(__uint_as_float(vr[j]), scv[jj], shv[jj]), 0.f);
+      const float4* w4 = reinterpret_cast<const float4*>(w1row + j * NCP);
+#pragma unroll
+      for (int k4 = 0; k4 < NC4; ++k4) {
+        const float4 w = w4[k4];
+        logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
+        logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
+        logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
+        logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
+      }
+    }
+  }
+}
+
+// all accumulator chunks of this warp's column share (chunks half, half + 2, ...) for one pixel row
+template <int NC4>
+__device__ __forceinline__ void final_row(uint32_t taddr0, int half, int nchunks, int n0, const float* pc0, const float* pc1,
+                                          const float* w1s, float (&logit)[NCP]) {
+  for (int ch = half; ch < nchunks; ch += 2) {
+    uint32_t vr[16];
+    ig::tmem_ld16(taddr0 + ch * 16, vr);
+    ig::tmem_ld_wait();
+    const int pci = (ch >> 1) * 16;
+    final_chunk<NC4>(vr, pc0 + pci, pc1 + pci, w1s + (n0 + ch * 16) * NCP, logit);
+  }
+}
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -464,34 +506,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // head: ~5400 clk per 256-pixel tile against ~650 clk of tensor work)
         const int nc4 = (a.nc + 3) >> 2;
         const int nchunks = a.block_n / 16;
-        for (int ch = half; ch < nchunks; ch += 2) {
-          uint32_t vr[16];
-          ig::tmem_ld16(taddr0 + ch * 16, vr);
-          ig::tmem_ld_wait();
-          const int col = n0 + ch * 16;
-          const int pci = (ch >> 1) * 16;
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 sc = *reinterpret_cast<const float4*>(pc0 + pci + 4 * j4);
-            const float4 sh = *reinterpret_cast<const float4*>(pc1 + pci + 4 * j4);
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = 4 * j4 + jj;
-              const float act = fmaxf(fmaf(__uint_as_float(vr[j]), scv[jj], shv[jj]), 0.f);
-              const float4* w4 = reinterpret_cast<const float4*>(w1s + (col + j) * NCP);
-#pragma unroll
-              for (int k4 = 0; k4 < NCP / 4; ++k4) {
-                if (k4 < nc4) {
-                  const float4 w = w4[k4];
-                  logit[4 * k4 + 0] = fmaf(act, w.x, logit[4 * k4 + 0]);
-                  logit[4 * k4 + 1] = fmaf(act, w.y, logit[4 * k4 + 1]);
-                  logit[4 * k4 + 2] = fmaf(act, w.z, logit[4 * k4 + 2]);
-                  logit[4 * k4 + 3] = fmaf(act, w.w, logit[4 * k4 + 3]);
-                }
-              }
-            }
-          }
+        switch (nc4) {   // kernel-uniform: one dispatch per tile
+          case 1: final_row<1>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
+          case 2: final_row<2>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
+          case 3: final_row<3>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
+          default: final_row<4>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
         }
         // accumulator fully read -> hand the TMEM stage back to the MMA warp
         ig::tc_fence_before();
