@@ -54,7 +54,9 @@ def gemm_traffic_from_profile():
     """Average DRAM bytes (read + write) per gemm_kernel launch of one bench step, from the committed ncu launch
     list of this same command (profiles/r01_launches_bench_step.csv: --metrics gpu__time_duration.sum,
     dram__bytes_read.sum,dram__bytes_write.sum).  None when the list is absent or has no DRAM columns."""
-    path = os.path.join(ROOT, "profiles", "r01_launches_bench_step.csv")
+    path = os.path.join(ROOT, "profiles", "r02_launches_bench_step.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_launches_bench_step.csv")
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import launch_summary
@@ -281,15 +283,23 @@ def tile_measure(model, pinned_tile, d_tile, rank, world, dev, stride, tile_batc
         torch.cuda.synchronize()
         fam = _lib.profile_report()
         _lib.profile_enable(False)
-    # end to end: pinned host tile in (each rank uploads only the raster rows it touches), host class map out
-    res = torch.empty((H, W), dtype=torch.int8).pin_memory()
+    # end to end: pinned host tile in (each rank uploads only the raster rows it touches, on a copy stream), host class
+    # map out (every rank brings the whole map back).  A stream of tiles: two pinned result buffers alternate and the
+    # host waits for the map of tile i-1 only after tile i has been enqueued, like ChipPipeline does for chip batches.
+    res = [torch.empty((H, W), dtype=torch.int8).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
     IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        res.copy_(IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw), non_blocking=True)
-        torch.cuda.synchronize()
+    for i in range(steps):
+        k = i & 1
+        if i >= 2:
+            done[k].synchronize()      # the buffer's previous map has reached the host (a consumer would read it here)
+        res[k].copy_(IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw), non_blocking=True)
+        done[k].record()
+    torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    res = res[(steps - 1) & 1]
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     return {"ms": ms, "windows": n_win, "windows_per_s": n_win / (ms / 1e3),
@@ -326,6 +336,66 @@ def tile_report(model, pinned_tile, rank, world, dev, steps, warmup, tile_batch=
         ok = ok and entry["same_as_host_path"] and min(entry["class_hist"]) > 0
         rep[f"stride{stride}"] = entry
     rep["ok"] = ok
+    return rep
+
+
+def v2_300m_report(rank, world, dev, steps, warmup):
+    """The `chips_v2_300m` key of the default bench line: BASELINE.json configs[2] (Prithvi-V2-300M, T = 3, 13 classes,
+    batch 128 per GPU, bf16) through the same step as the headline workload -- device-timed chips/s over all ranks --
+    and the first chip of the last timed batch against the fp32 CPU oracle on the model's own weights."""
+    import torch
+    import torch.distributed as dist
+    from instageo_b200 import ops
+    from instageo_b200.model import PrithviSeg
+    variant, t, nc, batch = "prithvi_eo_v2_300", 3, 13, 128
+    torch.manual_seed(0)
+    model = PrithviSeg(temporal_step=t, num_classes=nc, load_pretrained_weights=False, variant=variant)
+    stress_init(model, seed=2)
+    model = model.to(dev).eval()
+    spec = ops.PreprocessSpec(CROP_MEAN, CROP_STD, t, None, 1.0, None, dev)
+    cal = torch.randint(0, 10001, (8, t * 6, 224, 224), generator=torch.Generator().manual_seed(999), dtype=torch.int16)
+    calibrate_head_bias(model, ops.preprocess(cal.to(dev), spec, want_f32=False, want_patches=True)["patches"])
+    g = torch.Generator().manual_seed(2042 + rank)
+    raws = [torch.randint(0, 10001, (batch, t * 6, 224, 224), generator=g, dtype=torch.int16) for _ in range(2)]
+    d_raws = [r.to(dev) for r in raws]   # 2 x 231 MB of int16 + > 3 GB of activations per step: larger than L2
+
+    def step(i):
+        pre = ops.preprocess(d_raws[i & 1], spec, want_f32=False, want_patches=True)
+        return model.forward_patches(pre["patches"], want_logits=False, want_argmax=True)[1]
+
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        amax = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item() / steps
+    rep = {"workload": "prithvi_v2_300m_T3_nc13_b128 per GPU: raw int16 chips -> normalise/mask -> PrithviSeg -> argmax int8",
+           "value": world * batch / (ms / 1e3), "unit": "chips/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "forward_path": model.graph_status()}
+    if rank == 0:
+        from oracle import prithvi as P
+        idx = (steps - 1) & 1
+        pre = ops.preprocess(d_raws[idx], spec, want_f32=False, want_patches=True)
+        lg, am = model.forward_patches(pre["patches"], want_logits=True, want_argmax=True)
+        sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items() if v.is_floating_point()}
+        ref = cpu_oracle_logits(sd, raws[idx][:1].numpy(), P.VARIANTS[variant][2], t)
+        max_abs = (lg[:1].cpu() - ref).abs().max().item()
+        top2 = ref.topk(2, dim=1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 2 * max(max_abs, 1e-6)
+        agree = (am[:1].cpu().long() == ref.argmax(1))[safe].float().mean().item() if safe.any() else 0.0
+        rep["parity"] = {"chips": 1, "max_abs": max_abs, "tol": TOL, "argmax_agree_outside_ties": agree,
+                         "excluded": 1.0 - safe.float().mean().item(),
+                         "timed_batch_argmax_identical": bool(torch.equal(am, amax)),
+                         "ok": bool(max_abs < TOL and agree == 1.0 and torch.equal(am, amax))}
     return rep
 
 
@@ -665,7 +735,7 @@ def main():
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": gemm_traffic_from_profile() if args.workload == "chips_v1_100m_t3" else None,
                 "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, average over the "
-                                "57 gemm_kernel launches of one step, profiles/r01_launches_bench_step.csv)",
+                                "57 gemm_kernel launches of one step, profiles/r02_launches_bench_step.csv)",
                 "peak_source": peak_src,
                 "algorithmic_flops_per_launch": gemm_fl_step * args.steps / max(1, gemm_launches),
                 "avg_launch_ms": gemm_ms / max(1, gemm_launches), "share_of_step": gemm_ms / all_ms if all_ms else None,
@@ -720,12 +790,16 @@ def main():
         tile = tile_report(t_model, t_pinned, rank, world, dev, steps=max(2, min(5, args.steps)), warmup=2)
         out["tile"] = tile
         del t_model, t_pinned
+        torch.cuda.empty_cache()
+        out["chips_v2_300m"] = v2_300m_report(rank, world, dev, steps=max(2, min(5, args.steps)), warmup=3)
 
     ok = True
     if rank == 0:
         sd, raw_cpu, heads, cores = cpu_setup(model, raws[idx][:CPU_SAMPLE_CHIPS].numpy())
         out["parity"] = parity_report(model, sd, heads, raw_cpu[:PARITY_CHIPS], l_par, a_par, timed_identical)
         ok = out["parity"]["ok"] and (tile is None or tile["ok"])
+        if "chips_v2_300m" in out:
+            ok = ok and out["chips_v2_300m"]["parity"]["ok"]
         if world == 1 and not args.no_cpu_baseline:
             cpu_oracle_step(sd, raw_cpu[:1], heads)
             t0, n = time.perf_counter(), 0

@@ -310,8 +310,14 @@ class TileEngine:
         self._wins_rel = self._wins_abs.clone()
         if len(wl):
             self._wins_rel[:, 1] -= r0
-        self._d_tile = None     # [nb, r1 - r0, W] upload buffer (host input only)
-        self._d_fmask = None
+        # host input only: two [nb, r1 - r0, W] upload buffers filled on a copy stream, so the rows of tile i+1 travel
+        # while tile i is being computed (the host never waits inside run())
+        self._d_tile = [None, None]
+        self._slot = 0
+        self._copy_stream = None
+        self._in_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._in_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self._staged = None     # slot whose consumption by the compute stream has to be marked (in_free)
         n_own = o1 - o0
         self.n_calls = max(1, -(-n_own // self.batch_size)) if n_own else 0
         self.per_call = max(1, -(-n_own // self.n_calls)) if n_own else 0
@@ -347,19 +353,33 @@ class TileEngine:
                 fm = fm.to(self.device)
             return tile, 0, fm
         rows = self.r1 - self.r0
-        if self._d_tile is None:
-            self._d_tile = torch.empty((self.nb, max(1, rows), self.W), dtype=tile.dtype, device=self.device)
+        slot = self._slot
+        self._slot ^= 1
+        if self._d_tile[slot] is None:
+            self._d_tile[slot] = torch.empty((self.nb, max(1, rows), self.W), dtype=tile.dtype, device=self.device)
+        d_tile = self._d_tile[slot]
+        cur = torch.cuda.current_stream(self.device)
         if rows:
             src = tile[:, self.r0:self.r1]
-            if src.is_contiguous() or not tile.is_pinned():
-                self._d_tile[:, :rows].copy_(src, non_blocking=True)
-            else:   # pinned, strided over bands: one contiguous DMA per band (a strided copy would stage on the host)
-                for b in range(self.nb):
-                    self._d_tile[b, :rows].copy_(src[b], non_blocking=True)
+            if tile.is_pinned():
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(self.device)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(self._in_free[slot])   # the tile two calls ago has been consumed
+                    if src.is_contiguous():
+                        d_tile[:, :rows].copy_(src, non_blocking=True)
+                    else:   # strided over bands: one contiguous DMA per band (a strided copy would stage on the host)
+                        for b in range(self.nb):
+                            d_tile[b, :rows].copy_(src[b], non_blocking=True)
+                    self._in_ready[slot].record(self._copy_stream)
+                cur.wait_event(self._in_ready[slot])
+                self._staged = slot
+            else:
+                d_tile[:, :rows].copy_(src, non_blocking=True)   # pageable memory: a synchronous staged copy
         if fmask is not None:
             fm = fmask if isinstance(fmask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fmask))
             fm = fm[:, self.r0:self.r1].to(self.device, non_blocking=True)
-        return self._d_tile[:, :max(1, rows)], self.r0, fm
+        return d_tile[:, :max(1, rows)], self.r0, fm
 
     # -- one tile ------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -388,6 +408,9 @@ class TileEngine:
             if rows and (self.has_nodata or (fm is not None and self.fmask_bits)):
                 nd = ops.nodata_map(d_tile, self.spec, self.y0 - row_off, self.y1 - row_off, fmask=fm,
                                     fmask_bits=self.fmask_bits, masking_strategy=self.masking_strategy, out=self.nd)
+            if self._staged is not None:   # last reader of the upload buffer is enqueued: the slot may be refilled
+                self._in_free[self._staged].record(torch.cuda.current_stream(self.device))
+                self._staged = None
             for req in reqs:
                 req.wait()
             if rows:

@@ -93,7 +93,7 @@ def test_committed_bench_lines_follow_the_contract():
     """the bench lines kept under profiles/ carry every key the driver's contract names (bench.py docstring / DESIGN §6)"""
     import glob
     import json
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_*.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[12]_bench_*.json")))
     assert files, "no bench lines committed"
     for f in files:
         d = json.loads(open(f).read().strip().splitlines()[-1])
@@ -106,6 +106,15 @@ def test_committed_bench_lines_follow_the_contract():
         assert d["gpu_launches"] > 0 and d["value"] > 0 and d["vs_baseline"] is None
         bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         assert d["n_gpus"] > 1 or not (bad & set(d["clocks"]["reasons"])), (f, d["clocks"])
-    head = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_chips_v1.json")).read().strip().splitlines()[-1])
-    assert {"value", "unit", "cores", "kind", "sample"} <= set(head["cpu_baseline"])   # the driver's N = 1 line
-    assert head["roofline"]["bound"] == "tensor" and 0 < head["roofline"]["frac"] < 1
+    for name in ("r01_bench_chips_v1.json", "r02_bench_chips_v1.json"):
+        head = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(head["cpu_baseline"])   # the driver's N = 1 line
+        assert head["roofline"]["bound"] == "tensor" and 0 < head["roofline"]["frac"] < 1
+    # round 2: parity of the timed batch and the tile section travel in the same line
+    for name in ("r02_bench_chips_v1.json", "r02_bench_chips_v1_8gpu.json"):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert d["parity"]["ok"] and d["parity"]["max_abs"] < d["parity"]["tol"] and d["parity"]["timed_batch_argmax_identical"]
+        assert d["tile"]["ok"] and {"stride112", "stride224"} <= set(d["tile"])
+        assert min(d["tile"]["stride112"]["class_hist"]) > 0                     # nodata, class 0 and class 1 all present
+        if d["n_gpus"] > 1:
+            assert d["tile"]["stride112"]["bit_identical_to_single_gpu"] == {"window_exchange": True, "halo_recompute": True}
