@@ -504,9 +504,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // classes in groups of four: a 2-class (flood) or 1-channel (regression) head does a quarter of the 1x1
         // convolution's FMAs and weight loads of the padded NCP = 16 (this loop, not the UMMAs, bounded the T = 1
         // head: ~5400 clk per 256-pixel tile against ~650 clk of tensor work)
+#ifdef IG_FINAL_ABLATE   // timing ablation (wrong logits): how fast is the stage with a quarter / none of the class FMAs?
+        const int nc4 = IG_FINAL_ABLATE;
+#else
         const int nc4 = (a.nc + 3) >> 2;
+#endif
         const int nchunks = a.block_n / 16;
         switch (nc4) {   // kernel-uniform: one dispatch per tile
+          case 0: final_row<0>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
           case 1: final_row<1>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
           case 2: final_row<2>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;
           case 3: final_row<3>(taddr0, half, nchunks, n0, pc0, pc1, w1s, logit); break;

@@ -173,3 +173,22 @@ def test_tiles_bigtiff_and_byte_order(tmp_path, tile, big, endian, predictor):
     assert got.dtype == np.int16 and np.array_equal(got[0], a)
     want = cv2.imread(p, cv2.IMREAD_UNCHANGED)
     assert want is not None and np.array_equal(want, a)        # the handmade file itself is a valid TIFF
+
+
+def test_projected_crs_wins_over_geographic_key(tmp_path):
+    """GeoKey directories of older GDAL versions carry GeographicType (2048 = 4326) next to ProjectedCSType (3072 = the
+    UTM zone) for a projected CRS; keys are sorted by id, so 2048 comes first -- the profile must still report the UTM
+    code, on the host reader and on the layout shared with the device reader."""
+    a = np.arange(64, dtype=np.int16).reshape(8, 8)
+    geo = {33550: (30.0, 30.0, 0.0), 33922: (0.0, 0.0, 0.0, 318585.0, 4583115.0, 0.0),
+           34735: (1, 1, 0, 4, 1024, 0, 1, 1, 1025, 0, 1, 1, 2048, 0, 1, 4326, 3072, 0, 1, 32613)}
+    p = str(tmp_path / "both.tif")
+    G.write_geotiff(p, a, {"geo_tags": geo})
+    assert G.read_geotiff(p)[1]["crs_epsg"] == 32613
+    assert G._Layout(open(p, "rb").read()).profile("int16")["crs_epsg"] == 32613
+    geo[34735] = (1, 1, 0, 2, 1024, 0, 1, 2, 2048, 0, 1, 4326)          # geographic only
+    G.write_geotiff(p, a, {"geo_tags": geo})
+    assert G.read_geotiff(p)[1]["crs_epsg"] == 4326
+    geo[34735] = (1, 1, 0, 3, 1024, 0, 1, 1, 2048, 0, 1, 4326, 3072, 0, 1, 32767)   # user-defined projection: fall back
+    G.write_geotiff(p, a, {"geo_tags": geo})
+    assert G.read_geotiff(p)[1]["crs_epsg"] == 4326

@@ -99,3 +99,20 @@ def test_whole_tile_properties(cuda_dev):
     assert int(counts[0]) == int((o != 0).sum())
     again, _, counts2 = create_chip(o, fm, None, "each")   # idempotent
     assert torch.equal(again.view(torch.int16), o) and int(counts2[0]) == int(counts[0])
+
+
+def test_label_maps_are_not_silently_truncated(cuda_dev):
+    """The reference keeps the label map's dtype (float32 regression targets, hls_utils.py:398); the device kernel carries
+    int8 class labels: anything a cast would change is refused, int16 / int64 labels in range are taken."""
+    import numpy as np
+    import torch
+    from instageo_b200.data import create_chip
+    chip = np.random.default_rng(0).integers(0, 9000, size=(6, 32, 40)).astype(np.int16)
+    fm = np.zeros((1, 32, 40), np.uint8)
+    with pytest.raises(TypeError, match="integer class labels"):
+        create_chip(chip, fm, np.zeros((32, 40), np.float32))
+    with pytest.raises(ValueError, match="int8"):
+        create_chip(chip, fm, np.full((32, 40), 300, np.int32))
+    seg = np.random.default_rng(1).integers(-1, 100, size=(32, 40))
+    out = create_chip(chip, fm, seg.astype(np.int64))[1]
+    assert out.dtype == torch.int8 and np.array_equal(out.cpu().numpy(), seg.astype(np.int8))

@@ -155,3 +155,18 @@ def test_regression_metrics(cuda_dev, gold):
     ig.update(xi, y, ignore_value=-100.0)
     assert ig.n == int((xi != -100.0).sum())
     assert np.isnan(RunningRegressionMetrics(device=cuda_dev).mae())
+
+
+def test_out_of_range_predictions_need_no_host_round_trip(cuda_dev):
+    """non-int8 predictions are clamped on the device (an out-of-range value stays out of range and lands in the kernel's
+    counter); the ValueError of the reference surfaces at the first read-back, not through a .max() on the host"""
+    import numpy as np
+    import torch
+    from instageo_b200.model.metrics import RunningConfusionMatrix
+    cm = RunningConfusionMatrix(3, device=cuda_dev)
+    y = torch.tensor([0, 1, 2, 1], device=cuda_dev)
+    cm.update(y, torch.tensor([0, 1, 2, 2], device=cuda_dev, dtype=torch.int64))
+    assert cm.matrix.sum() == 4
+    cm.update(y, torch.tensor([0, 1, 2, 700], device=cuda_dev, dtype=torch.int32))
+    with pytest.raises(ValueError, match="outside"):
+        cm.matrix
