@@ -395,8 +395,23 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of a (possibly remote) CTA of the cluster.  Used to hand a TMEM accumulator stage back to the
+// pair leader's MMA warp: the tcgen05.ld's are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, so the
+// arrive itself needs no memory ordering.  The first version asked for .release.cluster, which ptxas turns into
+// MEMBAR.ALL.GPU (+ ERRBAR / CGAERRBAR): every epilogue warp then waited, once per tile, until the global stores of its
+// previous tile had been acknowledged -- the ~4-5 k clk of per-tile epilogue latency that bounded every short-K /
+// narrow-N tile.  IG_ARRIVE_SEM: 0 = .relaxed.cluster, 1 = the default .release.cta (shipped; what CUTLASS emits), 2 = .release.cluster (old).
+#ifndef IG_ARRIVE_SEM
+#define IG_ARRIVE_SEM 1
+#endif
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if IG_ARRIVE_SEM == 0
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#elif IG_ARRIVE_SEM == 1
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // TMA load issued by either CTA of a pair; completes on an mbarrier of the pair's leader
 // (`bar_cluster_addr` is a shared::cluster address).
