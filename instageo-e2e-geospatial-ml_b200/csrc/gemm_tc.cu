@@ -151,7 +151,7 @@ __device__ __forceinline__ void final_row(uint32_t taddr0, int half, int nchunks
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const Args a) {
+            const __grid_constant__ CUtensorMap tmAr, const __grid_constant__ CUtensorMap tmBr, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   // offset arithmetic on the __shared__ array itself (not a round trip through uintptr_t) keeps the pointer in
   // the shared address space: LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math
@@ -177,6 +177,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     ig::tma_prefetch_desc(&tmA);
     ig::tma_prefetch_desc(&tmB);
+    if (a.rem_cols) {
+      ig::tma_prefetch_desc(&tmAr);
+      ig::tma_prefetch_desc(&tmBr);
+    }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ig::mbar_init(&full[s], 1);    // leader: its own expect_tx arrive; bytes from both CTAs
       ig::mbar_init(&empty[s], 1);   // one multicast commit per use
@@ -217,15 +221,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const Taps& tp = a.taps[phase];
         for (int t = 0; t < tp.n; ++t) {
           const TapGroup& tg = tp.g[t];
-          const uint32_t tx_bytes = 2u * (a.a_box_rows * BK * 2 + tg.nsub * half_n * BK * 2);  // both CTAs' boxes
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+            // the last K block of a K that is not a multiple of 64 travels as 16- / 32-column boxes (a full box would
+            // move 4x / 2x the bytes its one or two UMMAs consume: the ring then starves the tensor pipe)
+            const bool narrow = a.rem_cols && kb == kblocks_per_tap - 1;
+            const int cols = narrow ? a.rem_cols : BK;
+            const uint32_t tx_bytes = 2u * (a.a_box_rows * cols * 2 + tg.nsub * half_n * cols * 2);  // both CTAs' boxes
             ig::mbar_wait(&empty[stage], ph ^ 1);
             if (rank == 0) ig::mbar_expect_tx(&full[stage], tx_bytes);
             const uint32_t bar = ig::mapa_u32(&full[stage], 0);
             uint8_t* sa = smem + stage * a.stage_bytes;
-            ig::tma_load_2d_cg2(sa, &tmA, bar, kb * BK, a.a_row_base + m0 + tg.a_off);
+            ig::tma_load_2d_cg2(sa, narrow ? &tmAr : &tmA, bar, kb * BK, a.a_row_base + m0 + tg.a_off);
             for (int sb = 0; sb < tg.nsub; ++sb)
-              ig::tma_load_2d_cg2(sa + a.a_bytes + sb * a.b_tap_bytes, &tmB, bar, tg.b_off[sb] + kb * BK, nb0);
+              ig::tma_load_2d_cg2(sa + a.a_bytes + sb * a.b_tap_bytes, narrow ? &tmBr : &tmB, bar, tg.b_off[sb] + kb * BK, nb0);
             if (++stage == a.num_stages) {
               stage = 0;
               ph ^= 1;
@@ -264,15 +272,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t sa = smem_base + stage * a.stage_bytes;
             const int krem = a.kc - kb * BK;
             const int nmma = krem >= BK ? BK / 16 : krem / 16;
+            // narrow last K block: rows of rem_cols bf16 (SWIZZLE_32B / 64B tiles), same K-major descriptor otherwise
+            const bool narrow = a.rem_cols && kb == kblocks_per_tap - 1;
+            const uint32_t row_bytes = narrow ? 2u * a.rem_cols : 128u;
+            const uint32_t hi = !narrow ? ig::UMMA_DESC_HI_SW128 : (a.rem_cols == 16 ? ig::UMMA_DESC_HI_SW32 : ig::UMMA_DESC_HI_SW64);
             if (ig::elect_one()) {
               for (int sb = 0; sb < nsub; ++sb) {
                 // row-shifted view of the shared A tile (start inside the swizzle atom, see ig_common.cuh)
-                const uint32_t a_lo = ig::umma_desc_lo(sa + tp.g[t].shift[sb] * 128);
+                const uint32_t a_lo = ig::umma_desc_lo(sa + tp.g[t].shift[sb] * row_bytes);
                 const uint32_t b_lo = ig::umma_desc_lo(sa + a.a_bytes + sb * a.b_tap_bytes);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                   if (k < nmma) {
-                    ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack(a_lo + 2 * k), ig::umma_desc_pack(b_lo + 2 * k),
+                    ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack_hi(a_lo + 2 * k, hi), ig::umma_desc_pack_hi(b_lo + 2 * k, hi),
                                       idesc, accumulate);
                     accumulate = 1;
                   }
@@ -588,7 +600,8 @@ static int launch_epi(const Plan& p, cudaStream_t stream) {
   const int max_pairs = ig_num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
   ig::ProfScope prof((EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) ? ig::PROF_GEMM_CONV : ig::PROF_GEMM_LINEAR, stream);
-  IG_CUDA_OK(ig::launch(gemm_kernel<EPI>, dim3(2 * pairs), dim3(THREADS), SMEM_TOTAL, stream, true, p.tmA, p.tmB, p.args));
+  IG_CUDA_OK(ig::launch(gemm_kernel<EPI>, dim3(2 * pairs), dim3(THREADS), SMEM_TOTAL, stream, true, p.tmA, p.tmB, p.tmAr,
+                        p.tmBr, p.args));
   return IG_OK;
 }
 
@@ -631,6 +644,8 @@ void finish_geometry(Args* a) {
     a->hw_magic = (one + hw - 1) / hw;
     a->wp_magic = (one + a->Wp - 1) / a->Wp;
   }
+  const int rem = a->kc % BK;
+  a->rem_cols = ((rem == 16 || rem == 32) && getenv("IG_NO_NARROW_K") == nullptr) ? rem : 0;
   a->a_bytes = (a->a_box_rows * BK * 2 + 1023) / 1024 * 1024;
   a->b_tap_bytes = ((a->block_n / 2) * BK * 2 + 1023) / 1024 * 1024;
   a->stage_bytes = a->a_bytes + maxsub * a->b_tap_bytes;
@@ -640,6 +655,19 @@ void finish_geometry(Args* a) {
     const int cap = atoi(e);
     if (cap >= 2 && cap < a->num_stages) a->num_stages = cap;
   }
+}
+
+int make_maps(Plan* p, const void* A, uint64_t a_rows, uint64_t lda, const void* W, uint64_t b_cols) {
+  const Args& a = p->args;
+  IG_TRY(ig_make_tmap_bf16(&p->tmA, A, a_rows, a.kc, lda, a.a_box_rows, BK));
+  IG_TRY(ig_make_tmap_bf16(&p->tmB, W, a.N, b_cols, b_cols, a.block_n / 2, BK));
+  p->tmAr = p->tmA;
+  p->tmBr = p->tmB;
+  if (a.rem_cols) {
+    IG_TRY(ig_make_tmap_bf16(&p->tmAr, A, a_rows, a.kc, lda, a.a_box_rows, a.rem_cols));
+    IG_TRY(ig_make_tmap_bf16(&p->tmBr, W, a.N, b_cols, b_cols, a.block_n / 2, a.rem_cols));
+  }
+  return IG_OK;
 }
 
 int pick_block_n(int N) {
@@ -672,8 +700,7 @@ int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int
   a.ldo = N;
   finish_geometry(&a);
   p->epi = epi;
-  IG_TRY(ig_make_tmap_bf16(&p->tmA, A, M, K, lda, a.a_box_rows, BK));
-  IG_TRY(ig_make_tmap_bf16(&p->tmB, W, N, K, K, a.block_n / 2, BK));
+  IG_TRY(make_maps(p, A, M, lda, W, K));
   return IG_OK;
 }
 

@@ -50,7 +50,7 @@ struct IgPerDevice {
 };
 
 // TMA descriptor for a row-major 2-D bf16 matrix [rows, cols] (cols contiguous), box
-// [box_rows, 64 cols], 128-byte swizzle.  row_pitch in elements.
+// [box_rows, box_cols], box_cols = 64 (128-byte swizzle), 32 (64-byte) or 16 (32-byte).  row_pitch in elements.
 int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_pitch, uint32_t box_rows, uint32_t box_cols);
 
@@ -278,12 +278,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 // Same descriptor as (lo, hi) words: only `lo` changes inside a K loop (start address >> 4, +2 per
 // 16 bf16 of K), `hi` is the constant SBO=1024 | version 1 | SWIZZLE_128B word.
 constexpr uint32_t UMMA_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+// K-major tiles whose rows are 64 / 32 bytes (32 / 16 bf16: the narrow last K block): 8-row groups 512 / 256 B apart,
+// layout type 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+constexpr uint32_t UMMA_DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+constexpr uint32_t UMMA_DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
   return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
 }
 __device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(UMMA_DESC_HI_SW128));
+  return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_pack_hi(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn,

@@ -47,6 +47,9 @@ struct Args {
   int a_row_base;  // guard rows in front of A (keeps shifted TMA coordinates >= 0)
   int a_box_rows;  // rows per A TMA box: 128, or 128 + A_HALO when taps are row-shifted
   int a_bytes, b_tap_bytes, stage_bytes, num_stages;  // operand ring geometry (host-computed)
+  int rem_cols;    // 16 | 32: K per tap is not a multiple of 64 and the LAST K block is loaded with boxes of that many
+                   // columns (SWIZZLE_32B / SWIZZLE_64B tiles through tmAr / tmBr) instead of a full 64-column box of which
+                   // a quarter / half is used; 0: every K block is a 64-column box
   Taps taps[4];
   const float* bias;   // bias, or BatchNorm scale for EPI_CONV / EPI_FINAL
   const float* shift;  // BatchNorm shift (with conv bias folded)
@@ -73,11 +76,14 @@ struct Args {
 
 struct Plan {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmAr, tmBr;  // narrow boxes of the last K block (copies of tmA / tmB when args.rem_cols == 0)
   Args args;
   int epi;
 };
 
 int launch(const Plan& p, cudaStream_t stream);
+// tensor maps of a plan (call after finish_geometry): A [a_rows, kc] pitch lda, B [N, b_cols] pitch b_cols
+int make_maps(Plan* p, const void* A, uint64_t a_rows, uint64_t lda, const void* W, uint64_t b_cols);
 
 // Plain linear: A [M,K] bf16 row-major (lda elements), W [N,K] bf16 row-major.
 int plan_linear(Plan* p, int epi, const void* A, int64_t lda, const void* W, int M, int N, int K);

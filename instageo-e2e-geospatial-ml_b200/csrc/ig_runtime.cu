@@ -94,14 +94,18 @@ int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   IG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IG_EINVAL, "TMA base %p not 16-byte aligned", base);
   IG_REQUIRE((row_pitch * 2) % 16 == 0, IG_ESHAPE, "TMA row pitch %llu elements not 16-byte aligned",
              static_cast<unsigned long long>(row_pitch));
-  IG_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols * 2 == 128, IG_ESHAPE,
-             "TMA box %ux%u unsupported (128-byte swizzle rows)", box_rows, box_cols);
+  IG_REQUIRE(box_rows >= 1 && box_rows <= 256 && (box_cols == 64 || box_cols == 32 || box_cols == 16), IG_ESHAPE,
+             "TMA box %ux%u unsupported (rows of 128, 64 or 32 bytes)", box_rows, box_cols);
+  // the swizzle span equals the box row: 64 columns = SWIZZLE_128B (every full K block), 32 / 16 columns = SWIZZLE_64B /
+  // SWIZZLE_32B (the narrow last K block of a K that is not a multiple of 64, see gemm::Args::rem_cols)
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {row_pitch * 2};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IG_REQUIRE(r == CUDA_SUCCESS, IG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)",
              static_cast<int>(r), static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols));

@@ -472,9 +472,8 @@ int plan_conv(gemm::Plan* p, int epi, const ig_model* m, char* ws, const Buf& in
   }
   gemm::finish_geometry(&a);
   p->epi = epi;
-  IG_TRY(ig_make_tmap_bf16(&p->tmA, ws + in.off, in.rows, Cin, Cin, a.a_box_rows, gemm::BK));
   const uint64_t wk = (stacked ? 4 : 9) * static_cast<uint64_t>(Cin);
-  IG_TRY(ig_make_tmap_bf16(&p->tmB, w, a.N, wk, wk, a.block_n / 2, gemm::BK));
+  IG_TRY(gemm::make_maps(p, ws + in.off, in.rows, Cin, w, wk));
   (void)m;
   return IG_OK;
 }
@@ -691,6 +690,7 @@ int enqueue(ig_model* m, ig_fwd_plan& fp, const FwdIO& io, cudaStream_t st, bool
     if (fp.patch_ext_src != io.x) {
       IG_TRY(ig_make_tmap_bf16(&fp.patch_ext.tmA, io.x, static_cast<uint64_t>(B) * T * g * g, m->K0, m->K0,
                                fp.patch_ext.args.a_box_rows, gemm::BK));
+      fp.patch_ext.tmAr = fp.patch_ext.tmA;   // K0 = 1536: no narrow K block
       fp.patch_ext_src = io.x;
     }
     pp = &fp.patch_ext;
@@ -842,19 +842,20 @@ int capture_graph(ig_model* m, ig_fwd_plan& fp, const FwdIO& io, unsigned flags,
 }
 
 // Re-point the two kernel nodes that carry caller pointers.  func / grid / block / shared memory are read back from
-// the captured node; the argument list (tmA, tmB, Args) is gemm_kernel's.
+// the captured node; the argument list (tmA, tmB, tmAr, tmBr, Args) is gemm_kernel's.
 int update_graph(ig_model* m, ig_fwd_plan& fp, GraphEntry& ge, const FwdIO& io) {
   cudaError_t e = cudaSuccess;
   if (io.x != ge.io.x) {
     if (fp.patch_ext_src != io.x) {
       IG_TRY(ig_make_tmap_bf16(&fp.patch_ext.tmA, io.x, static_cast<uint64_t>(fp.batch) * m->T * m->g * m->g, m->K0,
                                m->K0, fp.patch_ext.args.a_box_rows, gemm::BK));
+      fp.patch_ext.tmAr = fp.patch_ext.tmA;
       fp.patch_ext_src = io.x;
     }
     cudaKernelNodeParams kp;
     e = cudaGraphKernelNodeGetParams(ge.n_patch, &kp);
     if (e == cudaSuccess) {
-      void* args[3] = {&fp.patch_ext.tmA, &fp.patch_ext.tmB, &fp.patch_ext.args};
+      void* args[5] = {&fp.patch_ext.tmA, &fp.patch_ext.tmB, &fp.patch_ext.tmAr, &fp.patch_ext.tmBr, &fp.patch_ext.args};
       kp.kernelParams = args;
       kp.extra = nullptr;
       e = cudaGraphExecKernelNodeSetParams(ge.exec, ge.n_patch, &kp);
@@ -868,7 +869,7 @@ int update_graph(ig_model* m, ig_fwd_plan& fp, GraphEntry& ge, const FwdIO& io) 
     cudaKernelNodeParams kp;
     e = cudaGraphKernelNodeGetParams(ge.n_final, &kp);
     if (e == cudaSuccess) {
-      void* args[3] = {&fp.fin.tmA, &fp.fin.tmB, &fp.fin.args};
+      void* args[5] = {&fp.fin.tmA, &fp.fin.tmB, &fp.fin.tmAr, &fp.fin.tmBr, &fp.fin.args};
       kp.kernelParams = args;
       kp.extra = nullptr;
       e = cudaGraphExecKernelNodeSetParams(ge.exec, ge.n_final, &kp);
