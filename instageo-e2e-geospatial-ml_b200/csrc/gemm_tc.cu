@@ -93,11 +93,16 @@ __device__ __forceinline__ RowInfo make_row(const Args& a, int r, int phase) {
 // alone is 479 MB) instead of one pass.  The phase is rotated by the M tile so that a pair's tiles cycle
 // through the 1-, 2-, 2- and 4-tap phases instead of always getting the same two.
 __device__ __forceinline__ void decode_tile(const Args& a, int tile, int& phase, int& mt, int& nt) {
-  const int ph0 = tile % a.num_phases;
-  const int rest = tile / a.num_phases;
-  nt = rest % a.num_n_tiles;
-  mt = rest / a.num_n_tiles;
-  phase = (ph0 + mt) % a.num_phases;
+  // no hardware division: every role decodes every tile, and the four generic divisions this used to be (~600 clk of
+  // dependent MUFU.RCP / IMAD.HI chains) sat on the MMA warp's critical path between two tiles -- a third of the
+  // T = 1 final stage's tile period (tools/gemm_trace.py)
+  const unsigned int pm = static_cast<unsigned int>(a.num_phases - 1);
+  const unsigned int ph0 = static_cast<unsigned int>(tile) & pm;
+  const unsigned int rest = static_cast<unsigned int>(tile) >> a.phase_shift;
+  const unsigned int m = a.num_n_tiles == 1 ? rest : __umulhi(rest, a.nt_magic);
+  mt = static_cast<int>(m);
+  nt = static_cast<int>(rest - m * static_cast<unsigned int>(a.num_n_tiles));
+  phase = static_cast<int>((ph0 + m) & pm);
 }
 
 // 16-byte chunk `chunk` of staging row `row`, XOR-swizzled so that both the row-per-thread writes and
@@ -148,6 +153,26 @@ __device__ __forceinline__ void final_row(uint32_t taddr0, int half, int nchunks
   }
 }
 
+#ifndef IG_GEMM_ABLATE
+#define IG_GEMM_ABLATE 0
+#endif
+
+// Debug build only (-DIG_GEMM_TRACE=<epi>, tools/gemm_trace.py): SM-clock timestamps of the hand-offs between the three
+// warp roles of the leader CTA of pair 0, for the kernel instantiation EPI == IG_GEMM_TRACE.
+#ifdef IG_GEMM_TRACE
+__device__ unsigned long long g_trace[3][1 << 13];   // one region per role: plain stores, no atomics on the traced path
+#define IG_TRACE_DECL unsigned int trace_i = 0
+#define IG_TRACE(tag, tile)                                                                               \
+  do {                                                                                                    \
+    if (EPI == IG_GEMM_TRACE && blockIdx.x == 0 && trace_i < (1u << 13))                                  \
+      g_trace[((tag) >> 4) - 1][trace_i++] = (static_cast<unsigned long long>(clock64()) << 24) |         \
+                                             (static_cast<unsigned long long>((tile) & 0xffff) << 8) | (tag); \
+  } while (0)
+#else
+#define IG_TRACE_DECL do { } while (0)
+#define IG_TRACE(tag, tile) do { } while (0)
+#endif
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -167,6 +192,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* pcache = reinterpret_cast<float*>(smem + SMEM_MAIN + SMEM_STAGING + SMEM_W1 + SMEM_BARS);
 
   const int warp = ig::warp_idx_uniform(), lane = threadIdx.x & 31;
+  IG_TRACE_DECL;
   const uint32_t rank = ig::cluster_ctarank();       // 0 = leader of the pair
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int tiles_per_phase = a.num_m_tiles * a.num_n_tiles;
@@ -226,14 +252,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // move 4x / 2x the bytes its one or two UMMAs consume: the ring then starves the tensor pipe)
             const bool narrow = a.rem_cols && kb == kblocks_per_tap - 1;
             const int cols = narrow ? a.rem_cols : BK;
+#if IG_GEMM_ABLATE == 1   // timing ablation (wrong results): no B loads
+            const uint32_t tx_bytes = 2u * (a.a_box_rows * cols * 2);
+#elif IG_GEMM_ABLATE == 2  // no A loads
+            const uint32_t tx_bytes = 2u * (tg.nsub * half_n * cols * 2);
+#else
             const uint32_t tx_bytes = 2u * (a.a_box_rows * cols * 2 + tg.nsub * half_n * cols * 2);  // both CTAs' boxes
+#endif
             ig::mbar_wait(&empty[stage], ph ^ 1);
+            IG_TRACE(0x10, tile);   // producer: stage free, loads issued
             if (rank == 0) ig::mbar_expect_tx(&full[stage], tx_bytes);
             const uint32_t bar = ig::mapa_u32(&full[stage], 0);
             uint8_t* sa = smem + stage * a.stage_bytes;
+#if IG_GEMM_ABLATE != 2
             ig::tma_load_2d_cg2(sa, narrow ? &tmAr : &tmA, bar, kb * BK, a.a_row_base + m0 + tg.a_off);
+#endif
+#if IG_GEMM_ABLATE != 1
             for (int sb = 0; sb < tg.nsub; ++sb)
               ig::tma_load_2d_cg2(sa + a.a_bytes + sb * a.b_tap_bytes, narrow ? &tmBr : &tmB, bar, tg.b_off[sb] + kb * BK, nb0);
+#endif
             if (++stage == a.num_stages) {
               stage = 0;
               ph ^= 1;
@@ -262,13 +299,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const Taps& tp = a.taps[phase];
         ig::mbar_wait(&tempty[acc], acc_ph ^ 1);
         ig::tc_fence_after();
+        if (lane == 0) IG_TRACE(0x20, tile);   // MMA: accumulator slot free
         const uint32_t d_tmem = tmem_base + acc * MAX_BN;
-        uint32_t accumulate = 0;
+        // 0 for the tile's first UMMA only.  Warp-uniform and never written inside the elected region: as a per-lane
+        // variable it lived in a vector register and every UTCHMMA waited for an R2UR + UISETP chain of its own
+        uint32_t acc_first = 0;
         for (int t = 0; t < tp.n; ++t) {
           const int nsub = tp.g[t].nsub;
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
             ig::mbar_wait(&full[stage], ph);
             ig::tc_fence_after();
+            if (lane == 0) IG_TRACE(0x21, tile);   // MMA: stage data landed
             const uint32_t sa = smem_base + stage * a.stage_bytes;
             const int krem = a.kc - kb * BK;
             const int nmma = krem >= BK ? BK / 16 : krem / 16;
@@ -277,23 +318,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t row_bytes = narrow ? 2u * a.rem_cols : 128u;
             const uint32_t hi = !narrow ? ig::UMMA_DESC_HI_SW128 : (a.rem_cols == 16 ? ig::UMMA_DESC_HI_SW32 : ig::UMMA_DESC_HI_SW64);
             if (ig::elect_one()) {
-              for (int sb = 0; sb < nsub; ++sb) {
+              auto issue_sub = [&](int sb, uint32_t acc0) {
                 // row-shifted view of the shared A tile (start inside the swizzle atom, see ig_common.cuh)
                 const uint32_t a_lo = ig::umma_desc_lo(sa + tp.g[t].shift[sb] * row_bytes);
                 const uint32_t b_lo = ig::umma_desc_lo(sa + a.a_bytes + sb * a.b_tap_bytes);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
+#if IG_GEMM_ABLATE == 3   // one UMMA per stage
+                  if (k == 0 && sb == 0) {
+#else
                   if (k < nmma) {
+#endif
                     ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack_hi(a_lo + 2 * k, hi), ig::umma_desc_pack_hi(b_lo + 2 * k, hi),
-                                      idesc, accumulate);
-                    accumulate = 1;
+                                      idesc, k == 0 ? acc0 : 1u);
                   }
                 }
-              }
+              };
+              issue_sub(0, acc_first);
+              for (int sb = 1; sb < nsub; ++sb) issue_sub(sb, 1u);
               ig::umma_commit_cg2(&empty[stage], 3);  // frees the stage in both CTAs
             }
             __syncwarp();
-            accumulate = 1;
+            acc_first = 1;
+            if (lane == 0) IG_TRACE(0x23, tile);   // MMA: stage's UMMAs issued + committed
             if (++stage == a.num_stages) {
               stage = 0;
               ph ^= 1;
@@ -302,6 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (ig::elect_one()) ig::umma_commit_cg2(&tfull[acc], 3);  // accumulator ready in both CTAs
         __syncwarp();
+        if (lane == 0) IG_TRACE(0x22, tile);   // MMA: tile issued
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
       }
@@ -381,8 +429,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + g * GC));
         }
       }
+      if (ew == 0 && lane == 0) IG_TRACE(0x30, tile);   // epilogue warp 0: ready for the accumulator
       ig::mbar_wait(&tfull[acc], acc_ph);
       ig::tc_fence_after();
+      if (ew == 0 && lane == 0) IG_TRACE(0x31, tile);   // accumulator complete
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * MAX_BN;
 
       if (EPI != EPI_FINAL) {
@@ -533,6 +583,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ig::tc_fence_before();
         __syncwarp();
         if (lane == 0) ig::mbar_arrive_cluster(tempty_leader[acc]);
+        if (ew == 0 && lane == 0) IG_TRACE(0x32, tile);   // slot handed back
 
         float* ex = exch + (tile_par * BM + row_in_tile) * NCP;
         if (half == 1) {
@@ -571,6 +622,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tile_par ^= 1;
       }
+      if (ew == 0 && lane == 0) IG_TRACE(0x33, tile);   // tile stored
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
@@ -644,6 +696,8 @@ void finish_geometry(Args* a) {
     a->hw_magic = (one + hw - 1) / hw;
     a->wp_magic = (one + a->Wp - 1) / a->Wp;
   }
+  a->phase_shift = a->num_phases == 4 ? 2 : 0;
+  a->nt_magic = a->num_n_tiles > 1 ? static_cast<unsigned int>(((1ull << 32) + a->num_n_tiles - 1) / a->num_n_tiles) : 0u;
   const int rem = a->kc % BK;
   a->rem_cols = ((rem == 16 || rem == 32) && getenv("IG_NO_NARROW_K") == nullptr) ? rem : 0;
   a->a_bytes = (a->a_box_rows * BK * 2 + 1023) / 1024 * 1024;
@@ -669,6 +723,21 @@ int make_maps(Plan* p, const void* A, uint64_t a_rows, uint64_t lda, const void*
   }
   return IG_OK;
 }
+
+#ifdef IG_GEMM_TRACE
+}  // namespace gemm
+extern "C" int ig_debug_gemm_trace(unsigned long long* out, int cap, int reset) {
+  // out: [3][1 << 13] (zero entries = unused); reset clears the device buffer
+  const size_t bytes = sizeof(unsigned long long) * 3 * (1 << 13);
+  if (out && cap >= 3 * (1 << 13) && cudaMemcpyFromSymbol(out, gemm::g_trace, bytes) != cudaSuccess) return -1;
+  if (reset) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, gemm::g_trace) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) return -1;
+  }
+  return 3 * (1 << 13);
+}
+namespace gemm {
+#endif
 
 int pick_block_n(int N) {
   // largest multiple of 16 that divides N and fits one UMMA (<= 256)

@@ -60,6 +60,8 @@ struct Args {
   int tok_per_img, ntok;  // EPI_PATCH
   const float* pos;
   int Hp, Wp;             // padded input geometry of conv modes (H+2, W+2)
+  unsigned int nt_magic;   // ceil(2^32 / num_n_tiles) (num_n_tiles > 1): the tile decode's division as __umulhi
+  int phase_shift;         // log2(num_phases) (1 or 4 phases)
   unsigned long long hw_magic, wp_magic;  // ceil(2^48 / (Hp*Wp)), ceil(2^48 / Wp): exact division of a row index by
                                           // multiply-shift (n * d < 2^48), set by finish_geometry
   int out_guard;          // guard rows in front of the output buffer
