@@ -245,6 +245,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = mt * PAIR_M + static_cast<int>(rank) * BM;
         const int nb0 = nt * a.block_n + static_cast<int>(rank) * half_n;
         const Taps& tp = a.taps[phase];
+        if (a.units_per_stage > 1) {
+          // the tile's (tap group t, K block kb) units in order, units_per_stage of them per ring slot
+          const int units = tp.n * kblocks_per_tap;
+          int t = 0, kb = 0;
+          for (int u0 = 0; u0 < units; u0 += a.units_per_stage) {
+            const int nu = (units - u0) < a.units_per_stage ? (units - u0) : a.units_per_stage;
+            // the last K block of a K that is not a multiple of 64 travels as 16- / 32-column boxes (a full box would
+            // move 4x / 2x the bytes its one or two UMMAs consume)
+            uint32_t tx_bytes = 0;
+            for (int j = 0, tt = t, kk = kb; j < nu; ++j) {
+              const int cols = (a.rem_cols && kk == kblocks_per_tap - 1) ? a.rem_cols : BK;
+#if IG_GEMM_ABLATE == 1   // timing ablation (wrong results): no B loads
+              tx_bytes += 2u * (a.a_box_rows * cols * 2);
+#elif IG_GEMM_ABLATE == 2  // no A loads
+              tx_bytes += 2u * (tp.g[tt].nsub * half_n * cols * 2);
+#else
+              tx_bytes += 2u * (a.a_box_rows * cols * 2 + tp.g[tt].nsub * half_n * cols * 2);  // both CTAs' boxes
+#endif
+              if (++kk == kblocks_per_tap) {
+                kk = 0;
+                ++tt;
+              }
+            }
+            ig::mbar_wait(&empty[stage], ph ^ 1);
+            IG_TRACE(0x10, tile);   // producer: stage free, loads issued
+            if (rank == 0) ig::mbar_expect_tx(&full[stage], tx_bytes);
+            const uint32_t bar = ig::mapa_u32(&full[stage], 0);
+            for (int j = 0; j < nu; ++j) {
+              const TapGroup& tg = tp.g[t];
+              const bool narrow = a.rem_cols && kb == kblocks_per_tap - 1;
+              uint8_t* sa = smem + stage * a.stage_bytes + j * a.unit_bytes;
+#if IG_GEMM_ABLATE != 2
+              ig::tma_load_2d_cg2(sa, narrow ? &tmAr : &tmA, bar, kb * BK, a.a_row_base + m0 + tg.a_off);
+#endif
+#if IG_GEMM_ABLATE != 1
+              for (int sb = 0; sb < tg.nsub; ++sb)
+                ig::tma_load_2d_cg2(sa + a.a_bytes + sb * a.b_tap_bytes, narrow ? &tmBr : &tmB, bar, tg.b_off[sb] + kb * BK, nb0);
+#endif
+              if (++kb == kblocks_per_tap) {
+                kb = 0;
+                ++t;
+              }
+            }
+            if (++stage == a.num_stages) {
+              stage = 0;
+              ph ^= 1;
+            }
+          }
+          continue;
+        }
         for (int t = 0; t < tp.n; ++t) {
           const TapGroup& tg = tp.g[t];
           for (int kb = 0; kb < kblocks_per_tap; ++kb) {
@@ -304,46 +354,105 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // 0 for the tile's first UMMA only.  Warp-uniform and never written inside the elected region: as a per-lane
         // variable it lived in a vector register and every UTCHMMA waited for an R2UR + UISETP chain of its own
         uint32_t acc_first = 0;
-        for (int t = 0; t < tp.n; ++t) {
-          const int nsub = tp.g[t].nsub;
-          for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+        if (a.units_per_stage > 1) {
+          const int units = tp.n * kblocks_per_tap;
+          int t = 0, kb = 0;
+          for (int u0 = 0; u0 < units; u0 += a.units_per_stage) {
+            const int nu = (units - u0) < a.units_per_stage ? (units - u0) : a.units_per_stage;
             ig::mbar_wait(&full[stage], ph);
             ig::tc_fence_after();
             if (lane == 0) IG_TRACE(0x21, tile);   // MMA: stage data landed
-            const uint32_t sa = smem_base + stage * a.stage_bytes;
-            const int krem = a.kc - kb * BK;
-            const int nmma = krem >= BK ? BK / 16 : krem / 16;
-            // narrow last K block: rows of rem_cols bf16 (SWIZZLE_32B / 64B tiles), same K-major descriptor otherwise
-            const bool narrow = a.rem_cols && kb == kblocks_per_tap - 1;
-            const uint32_t row_bytes = narrow ? 2u * a.rem_cols : 128u;
-            const uint32_t hi = !narrow ? ig::UMMA_DESC_HI_SW128 : (a.rem_cols == 16 ? ig::UMMA_DESC_HI_SW32 : ig::UMMA_DESC_HI_SW64);
             if (ig::elect_one()) {
-              auto issue_sub = [&](int sb, uint32_t acc0) {
-                // row-shifted view of the shared A tile (start inside the swizzle atom, see ig_common.cuh)
-                const uint32_t a_lo = ig::umma_desc_lo(sa + tp.g[t].shift[sb] * row_bytes);
-                const uint32_t b_lo = ig::umma_desc_lo(sa + a.a_bytes + sb * a.b_tap_bytes);
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-#if IG_GEMM_ABLATE == 3   // one UMMA per stage
-                  if (k == 0 && sb == 0) {
+              int tt = t, kk = kb;   // lane-private walk; the warp's (t, kb) advance below, outside the elected region
+              for (int j = 0; j < nu; ++j) {
+                const uint32_t sa = smem_base + stage * a.stage_bytes + j * a.unit_bytes;
+                const int krem = a.kc - kk * BK;
+                const int nmma = krem >= BK ? BK / 16 : krem / 16;
+                // narrow last K block: rows of rem_cols bf16 (SWIZZLE_32B / 64B tiles), same K-major descriptor otherwise
+                const bool narrow = a.rem_cols && kk == kblocks_per_tap - 1;
+                const uint32_t row_bytes = narrow ? 2u * a.rem_cols : 128u;
+                const uint32_t hi = !narrow ? ig::UMMA_DESC_HI_SW128 : (a.rem_cols == 16 ? ig::UMMA_DESC_HI_SW32 : ig::UMMA_DESC_HI_SW64);
+                const TapGroup& tg = tp.g[tt];
+                auto issue_sub = [&](int sb, uint32_t acc0) {
+                  // row-shifted view of the shared A tile (start inside the swizzle atom, see ig_common.cuh)
+                  const uint32_t a_lo = ig::umma_desc_lo(sa + tg.shift[sb] * row_bytes);
+                  const uint32_t b_lo = ig::umma_desc_lo(sa + a.a_bytes + sb * a.b_tap_bytes);
+  #pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+#if IG_GEMM_ABLATE == 3   // one UMMA per unit
+                    if (k == 0 && sb == 0) {
 #else
-                  if (k < nmma) {
+                    if (k < nmma) {
 #endif
-                    ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack_hi(a_lo + 2 * k, hi), ig::umma_desc_pack_hi(b_lo + 2 * k, hi),
-                                      idesc, k == 0 ? acc0 : 1u);
+                      ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack_hi(a_lo + 2 * k, hi), ig::umma_desc_pack_hi(b_lo + 2 * k, hi),
+                                        idesc, k == 0 ? acc0 : 1u);
+                    }
                   }
+                };
+                issue_sub(0, j == 0 ? acc_first : 1u);
+                for (int sb = 1; sb < tg.nsub; ++sb) issue_sub(sb, 1u);
+                if (++kk == kblocks_per_tap) {
+                  kk = 0;
+                  ++tt;
                 }
-              };
-              issue_sub(0, acc_first);
-              for (int sb = 1; sb < nsub; ++sb) issue_sub(sb, 1u);
+              }
               ig::umma_commit_cg2(&empty[stage], 3);  // frees the stage in both CTAs
             }
             __syncwarp();
-            acc_first = 1;
             if (lane == 0) IG_TRACE(0x23, tile);   // MMA: stage's UMMAs issued + committed
+            kb += nu;
+            while (kb >= kblocks_per_tap) {
+              kb -= kblocks_per_tap;
+              ++t;
+            }
+            acc_first = 1;
             if (++stage == a.num_stages) {
               stage = 0;
               ph ^= 1;
+            }
+          }
+        } else {
+          for (int t = 0; t < tp.n; ++t) {
+            const int nsub = tp.g[t].nsub;
+            for (int kb = 0; kb < kblocks_per_tap; ++kb) {
+              ig::mbar_wait(&full[stage], ph);
+              ig::tc_fence_after();
+              if (lane == 0) IG_TRACE(0x21, tile);   // MMA: stage data landed
+              const uint32_t sa = smem_base + stage * a.stage_bytes;
+              const int krem = a.kc - kb * BK;
+              const int nmma = krem >= BK ? BK / 16 : krem / 16;
+              // narrow last K block: rows of rem_cols bf16 (SWIZZLE_32B / 64B tiles), same K-major descriptor otherwise
+              const bool narrow = a.rem_cols && kb == kblocks_per_tap - 1;
+              const uint32_t row_bytes = narrow ? 2u * a.rem_cols : 128u;
+              const uint32_t hi = !narrow ? ig::UMMA_DESC_HI_SW128 : (a.rem_cols == 16 ? ig::UMMA_DESC_HI_SW32 : ig::UMMA_DESC_HI_SW64);
+              if (ig::elect_one()) {
+                auto issue_sub = [&](int sb, uint32_t acc0) {
+                  // row-shifted view of the shared A tile (start inside the swizzle atom, see ig_common.cuh)
+                  const uint32_t a_lo = ig::umma_desc_lo(sa + tp.g[t].shift[sb] * row_bytes);
+                  const uint32_t b_lo = ig::umma_desc_lo(sa + a.a_bytes + sb * a.b_tap_bytes);
+  #pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+#if IG_GEMM_ABLATE == 3   // one UMMA per stage
+                    if (k == 0 && sb == 0) {
+#else
+                    if (k < nmma) {
+#endif
+                      ig::umma_bf16_cg2(d_tmem, ig::umma_desc_pack_hi(a_lo + 2 * k, hi), ig::umma_desc_pack_hi(b_lo + 2 * k, hi),
+                                        idesc, k == 0 ? acc0 : 1u);
+                    }
+                  }
+                };
+                issue_sub(0, acc_first);
+                for (int sb = 1; sb < nsub; ++sb) issue_sub(sb, 1u);
+                ig::umma_commit_cg2(&empty[stage], 3);  // frees the stage in both CTAs
+              }
+              __syncwarp();
+              acc_first = 1;
+              if (lane == 0) IG_TRACE(0x23, tile);   // MMA: stage's UMMAs issued + committed
+              if (++stage == a.num_stages) {
+                stage = 0;
+                ph ^= 1;
+              }
             }
           }
         }
@@ -702,7 +811,26 @@ void finish_geometry(Args* a) {
   a->rem_cols = ((rem == 16 || rem == 32) && getenv("IG_NO_NARROW_K") == nullptr) ? rem : 0;
   a->a_bytes = (a->a_box_rows * BK * 2 + 1023) / 1024 * 1024;
   a->b_tap_bytes = ((a->block_n / 2) * BK * 2 + 1023) / 1024 * 1024;
-  a->stage_bytes = a->a_bytes + maxsub * a->b_tap_bytes;
+  a->unit_bytes = a->a_bytes + maxsub * a->b_tap_bytes;
+  // Units per ring slot.  Each slot costs the MMA warp one full-barrier wait, one commit and ~400 clk of its own
+  // instruction latency (tools/gemm_trace.py), during which the tensor pipe drains its short queue.  Where a unit is a
+  // single K block of a narrow tile (the T = 1 final stage: K = 48, N = 48 -- nine ~60-clk UMMAs per unit) the whole
+  // tile's units go into one slot.  Everything else keeps one unit per slot: the generic packed loop costs the wide
+  // GEMMs ~8 % (same-box A/B), and packing gained nothing on stages with two or more K blocks per tap.
+  int max_units = 1;
+  for (int ph = 0; ph < a->num_phases; ++ph)
+    if (a->taps[ph].n > max_units) max_units = a->taps[ph].n;
+  a->units_per_stage = 1;
+  if (a->block_n <= 64 && a->kc <= BK) {
+    int u = SMEM_MAIN / (2 * a->unit_bytes);
+    if (u > max_units) u = max_units;
+    if (u > 1) a->units_per_stage = u;
+  }
+  if (const char* e = getenv("IG_GEMM_UNITS")) {  // measurement aid
+    const int u = atoi(e);
+    if (u >= 1 && SMEM_MAIN / (u * a->unit_bytes) >= 2) a->units_per_stage = u;
+  }
+  a->stage_bytes = a->units_per_stage * a->unit_bytes;
   a->num_stages = SMEM_MAIN / a->stage_bytes;
   if (a->num_stages > MAX_STAGES) a->num_stages = MAX_STAGES;
   if (const char* e = getenv("IG_GEMM_STAGES")) {  // measurement aid: cap the operand ring depth

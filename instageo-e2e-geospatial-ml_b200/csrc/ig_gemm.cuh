@@ -47,6 +47,8 @@ struct Args {
   int a_row_base;  // guard rows in front of A (keeps shifted TMA coordinates >= 0)
   int a_box_rows;  // rows per A TMA box: 128, or 128 + A_HALO when taps are row-shifted
   int a_bytes, b_tap_bytes, stage_bytes, num_stages;  // operand ring geometry (host-computed)
+  int unit_bytes, units_per_stage;  // a ring slot (stage) carries up to units_per_stage (tap group, K block) units of
+                                    // unit_bytes = A box + max-nsub B boxes each: one full / empty hand-off for all of them
   int rem_cols;    // 16 | 32: K per tap is not a multiple of 64 and the LAST K block is loaded with boxes of that many
                    // columns (SWIZZLE_32B / SWIZZLE_64B tiles through tmAr / tmBr) instead of a full 64-column box of which
                    // a quarter / half is used; 0: every K block is a 64-column box
