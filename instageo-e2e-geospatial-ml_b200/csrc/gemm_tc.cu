@@ -176,7 +176,8 @@ __device__ unsigned long long g_trace[3][1 << 13];   // one region per role: pla
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmAr, const __grid_constant__ CUtensorMap tmBr, const Args a) {
+            const __grid_constant__ CUtensorMap tmAr, const __grid_constant__ CUtensorMap tmBr,
+            const __grid_constant__ CUtensorMap tmO, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   // offset arithmetic on the __shared__ array itself (not a round trip through uintptr_t) keeps the pointer in
   // the shared address space: LDS/STS with 32-bit addresses instead of generic LD/ST with 64-bit address math
@@ -530,7 +531,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (ob >= 0 && ch < nchunk) extra[it] = *reinterpret_cast<const float4*>(a.resid + ob + col0 + ch * EPC);
         }
       };
-      if (EPI == EPI_RESID) {
+      // in-place residual through bulk reductions: nothing to load (see the store section)
+      const bool out_tma = EPI == EPI_RESID && a.out_tma;
+      if (EPI == EPI_RESID && !out_tma) {
         if (half < ngroups) load_resid(half);
         if (ri.valid) {
           const float* rrow = a.resid + static_cast<long long>(ri.orow) * a.ldo + n0;
@@ -559,6 +562,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) ig::mbar_arrive_cluster(tempty_leader[acc]);
             released = true;
+          }
+          if (out_tma) {   // the previous group's reduction must have read the staging tile before it is rewritten
+            if (lane == 0) ig::bulk_wait_read_all();
+            __syncwarp();
           }
 #pragma unroll
           for (int u = 0; u < GC / 16; ++u) {
@@ -611,6 +618,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
+          if (out_tma) {
+            // x += staging tile [32 rows x 32 f32] (the XOR layout of stg_slot IS the 128-byte TMA swizzle): one bulk
+            // tensor reduction per column group.  The L2 performs the adds; the SM neither loads the residual (the
+            // old epilogue moved 256 KB per tile through registers and took 4x the K = 768 projection's UMMA time,
+            // ncu: 32 % tensor pipe) nor stores the sum.  Each element is touched by exactly one reduction per launch,
+            // so the result is order-independent; rows >= M are clipped by the tensor map.
+            ig::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ig::tma_reduce_add_2d(&tmO, stg, n0 + col0, m0 + quad * 32);
+              ig::bulk_commit_group();
+            }
+            continue;
+          }
           __syncwarp();
           // coalesced write-out: 8 lanes cover one 128-byte row piece, 4 rows per instruction.
           // All residual / pos-embed loads are issued before the first store: `out` may alias
@@ -659,7 +680,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + offs[it]) = q;
             }
           }
-          if (EPI == EPI_RESID && g + 2 < ngroups) load_resid(g + 2);  // other columns than the stores above
+          if (EPI == EPI_RESID && !out_tma && g + 2 < ngroups) load_resid(g + 2);  // other columns than the stores above
           __syncwarp();
         }
         if (!released) {  // warp had no column group in this tile (ngroups == 1, half == 1)
@@ -737,6 +758,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if (EPI == EPI_RESID && a.out_tma && warp >= 2 && lane == 0) ig::bulk_wait_read_all();  // staging tiles still being read
   // No CTA of the pair may exit (or free TMEM) while its peer can still read its shared memory,
   // signal its barriers or write its accumulators.
   ig::tc_fence_before();
@@ -762,7 +784,7 @@ static int launch_epi(const Plan& p, cudaStream_t stream) {
   const int pairs = total < max_pairs ? total : max_pairs;
   ig::ProfScope prof((EPI == EPI_CONV || EPI == EPI_CONVT || EPI == EPI_FINAL) ? ig::PROF_GEMM_CONV : ig::PROF_GEMM_LINEAR, stream);
   IG_CUDA_OK(ig::launch(gemm_kernel<EPI>, dim3(2 * pairs), dim3(THREADS), SMEM_TOTAL, stream, true, p.tmA, p.tmB, p.tmAr,
-                        p.tmBr, p.args));
+                        p.tmBr, p.tmO, p.args));
   return IG_OK;
 }
 
@@ -845,6 +867,7 @@ int make_maps(Plan* p, const void* A, uint64_t a_rows, uint64_t lda, const void*
   IG_TRY(ig_make_tmap_bf16(&p->tmB, W, a.N, b_cols, b_cols, a.block_n / 2, BK));
   p->tmAr = p->tmA;
   p->tmBr = p->tmB;
+  p->tmO = p->tmA;
   if (a.rem_cols) {
     IG_TRY(ig_make_tmap_bf16(&p->tmAr, A, a_rows, a.kc, lda, a.a_box_rows, a.rem_cols));
     IG_TRY(ig_make_tmap_bf16(&p->tmBr, W, a.N, b_cols, b_cols, a.block_n / 2, a.rem_cols));
@@ -866,6 +889,21 @@ extern "C" int ig_debug_gemm_trace(unsigned long long* out, int cap, int reset) 
 }
 namespace gemm {
 #endif
+
+int set_residual_inplace(Plan* p, float* x) {
+  Args& a = p->args;
+  IG_REQUIRE(p->epi == EPI_RESID && x != nullptr, IG_EINVAL, "gemm: in-place residual needs an EPI_RESID plan");
+  a.resid = x;
+  a.out = x;
+  a.out_tma = 0;
+  if (a.block_n % 32 == 0 && a.N % 32 == 0 && a.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      getenv("IG_NO_RESID_TMA") == nullptr) {
+    IG_TRY(ig_make_tmap_f32_tile(&p->tmO, x, static_cast<uint64_t>(a.M), static_cast<uint64_t>(a.N),
+                                 static_cast<uint64_t>(a.ldo), 32));
+    a.out_tma = 1;
+  }
+  return IG_OK;
+}
 
 int pick_block_n(int N) {
   // largest multiple of 16 that divides N and fits one UMMA (<= 256)
@@ -917,5 +955,6 @@ extern "C" int ig_linear(const void* A, const void* W, const float* bias, const 
   p.args.resid = resid;
   p.args.act = act;
   p.args.out = out;
+  if (resid && resid == out) IG_TRY(gemm::set_residual_inplace(&p, static_cast<float*>(out)));
   return gemm::launch(p, static_cast<cudaStream_t>(stream));
 }

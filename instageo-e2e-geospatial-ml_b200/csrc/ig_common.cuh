@@ -51,6 +51,9 @@ struct IgPerDevice {
 
 // TMA descriptor for a row-major 2-D bf16 matrix [rows, cols] (cols contiguous), box
 // [box_rows, box_cols], box_cols = 64 (128-byte swizzle), 32 (64-byte) or 16 (32-byte).  row_pitch in elements.
+// f32 [rows, cols] row-major, box [box_rows, 32 columns] = 128-byte rows, 128-byte swizzle (epilogue staging tiles)
+int ig_make_tmap_f32_tile(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch,
+                          uint32_t box_rows);
 int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_pitch, uint32_t box_rows, uint32_t box_cols);
 
@@ -200,6 +203,15 @@ __device__ __forceinline__ int warp_idx_uniform() {
 }
 
 // ---- proxies / fences
+// ---- bulk tensor reduction shared -> global (f32 add performed by the L2, element by element; no read into the SM)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's committed bulk groups have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -47,6 +47,8 @@ struct Args {
   int a_row_base;  // guard rows in front of A (keeps shifted TMA coordinates >= 0)
   int a_box_rows;  // rows per A TMA box: 128, or 128 + A_HALO when taps are row-shifted
   int a_bytes, b_tap_bytes, stage_bytes, num_stages;  // operand ring geometry (host-computed)
+  int out_tma;     // EPI_RESID with out == resid: the epilogue adds (acc + bias) INTO the f32 stream with bulk tensor
+                   // reductions (cp.reduce.async.bulk.tensor .add) from its staging tiles instead of loading the residual
   int unit_bytes, units_per_stage;  // a ring slot (stage) carries up to units_per_stage (tap group, K block) units of
                                     // unit_bytes = A box + max-nsub B boxes each: one full / empty hand-off for all of them
   int rem_cols;    // 16 | 32: K per tap is not a multiple of 64 and the LAST K block is loaded with boxes of that many
@@ -81,12 +83,16 @@ struct Args {
 struct Plan {
   CUtensorMap tmA, tmB;
   CUtensorMap tmAr, tmBr;  // narrow boxes of the last K block (copies of tmA / tmB when args.rem_cols == 0)
+  CUtensorMap tmO;         // f32 output as [32-row, 32-column] tiles (args.out_tma; a copy of tmA otherwise)
   Args args;
   int epi;
 };
 
 int launch(const Plan& p, cudaStream_t stream);
 // tensor maps of a plan (call after finish_geometry): A [a_rows, kc] pitch lda, B [N, b_cols] pitch b_cols
+// EPI_RESID in place (x += A W^T + bias): sets resid = out = x and the output tensor map.  Falls back to the load /
+// add / store epilogue (out_tma = 0) where the tile shape does not allow the bulk reduction.
+int set_residual_inplace(Plan* p, float* x);
 int make_maps(Plan* p, const void* A, uint64_t a_rows, uint64_t lda, const void* W, uint64_t b_cols);
 
 // Plain linear: A [M,K] bf16 row-major (lda elements), W [N,K] bf16 row-major.

@@ -112,6 +112,25 @@ int ig_make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return IG_OK;
 }
 
+int ig_make_tmap_f32_tile(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch,
+                          uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  IG_REQUIRE(enc != nullptr, IG_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  IG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, IG_EINVAL, "TMA base %p not 16-byte aligned", base);
+  IG_REQUIRE((row_pitch * 4) % 16 == 0 && cols % 32 == 0 && box_rows >= 1 && box_rows <= 256, IG_ESHAPE,
+             "f32 TMA tile: pitch %llu / cols %llu / box rows %u unsupported", static_cast<unsigned long long>(row_pitch),
+             static_cast<unsigned long long>(cols), box_rows);
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {row_pitch * 4};
+  const cuuint32_t box[2] = {32, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IG_REQUIRE(r == CUDA_SUCCESS, IG_ECUDA, "cuTensorMapEncodeTiled (f32 tile) failed with CUresult %d", static_cast<int>(r));
+  return IG_OK;
+}
+
 int ig_make_tmap_nd(CUtensorMap* map, int dtype, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();

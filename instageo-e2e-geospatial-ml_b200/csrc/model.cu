@@ -572,16 +572,14 @@ int build_plan(ig_model* m, int batch, char* ws, ig_fwd_plan** out) {
     p[0].args.out = qkv;
     PLAN_TRY(gemm::plan_linear(&p[1], gemm::EPI_RESID, att, D, w.proj_w, M, D, D));
     p[1].args.bias = w.proj_b;
-    p[1].args.resid = xres;
-    p[1].args.out = xres;
+    PLAN_TRY(gemm::set_residual_inplace(&p[1], xres));
     PLAN_TRY(gemm::plan_linear(&p[2], gemm::EPI_BF16, xn, D, w.fc1_w, M, 4 * D, D));
     p[2].args.bias = w.fc1_b;
     p[2].args.act = 1;
     p[2].args.out = hid;
     PLAN_TRY(gemm::plan_linear(&p[3], gemm::EPI_RESID, hid, 4 * D, w.fc2_w, M, D, 4 * D));
     p[3].args.bias = w.fc2_b;
-    p[3].args.resid = xres;
-    p[3].args.out = xres;
+    PLAN_TRY(gemm::set_residual_inplace(&p[3], xres));
   }
   if (m->L > 0) PLAN_TRY(ops::attention_maps(qkv, B, N, m->heads, &fp->tmq, &fp->tmkv));
   const Buf* in = &l.in0;
@@ -842,7 +840,7 @@ int capture_graph(ig_model* m, ig_fwd_plan& fp, const FwdIO& io, unsigned flags,
 }
 
 // Re-point the two kernel nodes that carry caller pointers.  func / grid / block / shared memory are read back from
-// the captured node; the argument list (tmA, tmB, tmAr, tmBr, Args) is gemm_kernel's.
+// the captured node; the argument list (tmA, tmB, tmAr, tmBr, tmO, Args) is gemm_kernel's.
 int update_graph(ig_model* m, ig_fwd_plan& fp, GraphEntry& ge, const FwdIO& io) {
   cudaError_t e = cudaSuccess;
   if (io.x != ge.io.x) {
@@ -855,7 +853,8 @@ int update_graph(ig_model* m, ig_fwd_plan& fp, GraphEntry& ge, const FwdIO& io) 
     cudaKernelNodeParams kp;
     e = cudaGraphKernelNodeGetParams(ge.n_patch, &kp);
     if (e == cudaSuccess) {
-      void* args[5] = {&fp.patch_ext.tmA, &fp.patch_ext.tmB, &fp.patch_ext.tmAr, &fp.patch_ext.tmBr, &fp.patch_ext.args};
+      void* args[6] = {&fp.patch_ext.tmA, &fp.patch_ext.tmB, &fp.patch_ext.tmAr, &fp.patch_ext.tmBr, &fp.patch_ext.tmO,
+                       &fp.patch_ext.args};
       kp.kernelParams = args;
       kp.extra = nullptr;
       e = cudaGraphExecKernelNodeSetParams(ge.exec, ge.n_patch, &kp);
@@ -869,7 +868,7 @@ int update_graph(ig_model* m, ig_fwd_plan& fp, GraphEntry& ge, const FwdIO& io) 
     cudaKernelNodeParams kp;
     e = cudaGraphKernelNodeGetParams(ge.n_final, &kp);
     if (e == cudaSuccess) {
-      void* args[5] = {&fp.fin.tmA, &fp.fin.tmB, &fp.fin.tmAr, &fp.fin.tmBr, &fp.fin.args};
+      void* args[6] = {&fp.fin.tmA, &fp.fin.tmB, &fp.fin.tmAr, &fp.fin.tmBr, &fp.fin.tmO, &fp.fin.args};
       kp.kernelParams = args;
       kp.extra = nullptr;
       e = cudaGraphExecKernelNodeSetParams(ge.exec, ge.n_final, &kp);

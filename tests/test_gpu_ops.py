@@ -25,6 +25,25 @@ def test_linear_tcgen05(cuda_dev, M, N, K):
     assert (ops.linear(a, w, b, resid=r) - want).abs().max().item() < 1e-3 * scale
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 768), (37696, 768, 768), (301, 1024, 4096), (64, 64, 64)])
+def test_linear_inplace_residual_reduction(cuda_dev, M, N, K, monkeypatch):
+    """x += a @ w.T + b: the bulk-tensor-reduction epilogue (the L2 adds the staged tile into x) gives bit for bit what
+    the load / add / store epilogue gives, including the partial last row tile and several tiles per CTA pair."""
+    from instageo_b200 import ops
+    g = torch.Generator().manual_seed(N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(cuda_dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda_dev).bfloat16()
+    b = torch.randn(N, generator=g).to(cuda_dev)
+    x0 = torch.randn(M, N, generator=g).to(cuda_dev)
+    got = ops.linear(a, w, b, resid=x0.clone())
+    monkeypatch.setenv("IG_NO_RESID_TMA", "1")
+    want = ops.linear(a, w, b, resid=x0.clone())
+    monkeypatch.delenv("IG_NO_RESID_TMA")
+    assert torch.equal(got, want)
+    ref = x0 + a.float() @ w.float().t() + b
+    assert (got - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("D", [256, 768, 1024])
 def test_layernorm(cuda_dev, D):
     from instageo_b200 import ops

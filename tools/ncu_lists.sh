@@ -10,4 +10,4 @@ echo "bench list rc=$?"
 timeout 600 ncu --metrics $M --clock-control none -c 1500 --csv --log-file gpurun_out/r02_launches_tile224.csv \
   python bench.py --workload tile_3660 --stride 224 --steps 1 --warmup 1 > gpurun_out/ncu_tile.log 2>&1
 echo "tile list rc=$?"
-tail -2 gpurun_out/ncu_bench.log gpurun_out/ncu_tile.log
+tail -n 2 gpurun_out/ncu_bench.log; tail -n 2 gpurun_out/ncu_tile.log
