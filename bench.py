@@ -787,7 +787,7 @@ def main():
     if args.workload == "chips_v1_100m_t3" and not args.no_tile:
         del pipe, pinned
         t_model, t_pinned = tile_setup(dev)
-        tile = tile_report(t_model, t_pinned, rank, world, dev, steps=max(2, min(5, args.steps)), warmup=2)
+        tile = tile_report(t_model, t_pinned, rank, world, dev, steps=max(2, min(10, args.steps)), warmup=2)
         out["tile"] = tile
         del t_model, t_pinned
         torch.cuda.empty_cache()

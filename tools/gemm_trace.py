@@ -18,19 +18,34 @@ import instageo_b200  # noqa: E402,F401
 from instageo_b200 import _lib  # noqa: E402
 from instageo_b200.model import PrithviSeg  # noqa: E402
 
-T, nc, B = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (1, 2, 145)
-first, ntiles = (int(v) for v in sys.argv[4:6]) if len(sys.argv) > 5 else (20, 4)
 lib = ctypes.CDLL(os.environ["INSTAGEO_B200_LIB"])
 lib.ig_debug_gemm_trace.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-m = PrithviSeg(temporal_step=T, num_classes=nc, load_pretrained_weights=False).to(dev).eval()
-patches = torch.randn(B * T * 196, 1536, device=dev).bfloat16()
+if len(sys.argv) > 1 and sys.argv[1] == "linear":
+    # one plain GEMM instead of a forward: linear M N K resid(0|1) [first_tile ntiles]  (EPI 2 with resid, else EPI 0)
+    from instageo_b200 import ops  # noqa: E402
+    M, N, K, with_resid = (int(v) for v in sys.argv[2:6])
+    first, ntiles = (int(v) for v in sys.argv[6:8]) if len(sys.argv) > 7 else (2, 2)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    x = torch.randn(M, N, device=dev)
+
+    def run():
+        return ops.linear(a, w, None, resid=x) if with_resid else ops.linear(a, w, None)
+else:
+    T, nc, B = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (1, 2, 145)
+    first, ntiles = (int(v) for v in sys.argv[4:6]) if len(sys.argv) > 5 else (20, 4)
+    m = PrithviSeg(temporal_step=T, num_classes=nc, load_pretrained_weights=False).to(dev).eval()
+    patches = torch.randn(B * T * 196, 1536, device=dev).bfloat16()
+
+    def run():
+        return m.forward_patches(patches, want_logits=True, want_argmax=True)
 for _ in range(3):
-    m.forward_patches(patches, want_logits=True, want_argmax=True)
+    run()
 torch.cuda.synchronize()
 lib.ig_debug_gemm_trace(None, 0, 1)
-m.forward_patches(patches, want_logits=True, want_argmax=True)
+run()
 torch.cuda.synchronize()
 buf = np.zeros(3 << 13, dtype=np.uint64)
 lib.ig_debug_gemm_trace(buf.ctypes.data, buf.size, 1)
