@@ -387,7 +387,12 @@ class TileEngine:
         """int8 class map: the whole [H, W] map when ``gather`` (all ranks end up with it), else this rank's stripe
         [y1-y0, W].  The returned tensor is a VIEW of the engine's buffer: valid until the next ``run``."""
         with torch.cuda.device(self.device):
+            mark = self._mark if self.timing else (lambda name: None)
+            if self.timing:
+                self._marks = []
+            mark("start")
             d_tile, row_off, fm = self._stage(hls_tile, fmask)
+            mark("input staged")
             wins = self._wins_rel if row_off else self._wins_abs
             raw4 = d_tile.unsqueeze(0)
             fm4 = None if fm is None else fm.unsqueeze(0)
@@ -401,6 +406,7 @@ class TileEngine:
                                      want_patches=True, fmask=fm4, fmask_bits=self.fmask_bits,
                                      masking_strategy=self.masking_strategy, out_patches=self.patches)
                 self.model.forward_patches(pre["patches"], want_logits=True, out_logits=self.logits[base + s:base + e])
+            mark("preprocess + model")
             reqs = _exchange(self.logits, self.u0, self.logits, self.u0, self.sends, self.recvs, self.world) \
                 if (self.sends or self.recvs) else []
             rows = self.y1 - self.y0
@@ -413,14 +419,32 @@ class TileEngine:
                 self._staged = None
             for req in reqs:
                 req.wait()
+            mark("window-logit exchange (+ nodata map)")
             if rows:
                 n0, n1 = self.need
                 ops.stitch(self.logits[n0 - self.u0:n1 - self.u0], self.ys, self.xs, self.H, self.W, y0=self.y0,
                            y1=self.y1, win_base=n0, nodata_px=nd, nodata_class=self.nodata_class,
                            origins=self.origins, out=self.out)
+            mark("stitch")
             if not gather or self.world == 1:
                 return self.out
-            return self._gather()
+            full = self._gather()
+            mark("stripe all-gather")
+            return full
+
+    # -- optional device-side phase timing (tools/tile_phases.py) ---------------------------------------------------
+    timing = False
+
+    def _mark(self, name: str) -> None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self._marks.append((name, ev))
+
+    def phase_ms(self) -> "dict[str, float]":
+        """Milliseconds between consecutive marks of the last ``run`` (``timing = True``); synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        m = getattr(self, "_marks", [])
+        return {m[i][0]: m[i - 1][1].elapsed_time(m[i][1]) for i in range(1, len(m))}
 
     def _gather(self) -> torch.Tensor:
         import torch.distributed as dist
