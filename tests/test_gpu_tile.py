@@ -147,6 +147,16 @@ def test_tile_engine_host_rows_and_device_tile_agree(cuda_dev):
                 assert torch.equal(part, full[y0:y1])
     # world_size 1 through the sharded entry (in-place gather buffer, no collective)
     assert torch.equal(IU.sliding_window_inference_sharded(pinned, m, 0, 1, **kw), full)
+    # optional per-phase device timing (tools/tile_phases.py): same result, one positive duration per phase
+    engines = [e for e in IU._ENGINES.values() if e.model is m]
+    for e in engines:
+        e.timing, e._marks = True, []
+    assert torch.equal(IU.sliding_window_inference_sharded(d_tile, m, 0, 1, **kw), full)
+    ph = next(e for e in engines if e._marks).phase_ms()
+    for e in engines:
+        e.timing = False
+    assert list(ph) == ["input staged", "preprocess + model", "window-logit exchange (+ nodata map)", "stitch"]
+    assert all(v >= 0 for v in ph.values()) and ph["preprocess + model"] > 0
 
 
 def test_sharded_tile_is_bit_identical_across_gpu_counts():
