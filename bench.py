@@ -288,16 +288,16 @@ def tile_measure(model, pinned_tile, d_tile, rank, world, dev, stride, tile_batc
     # host waits for the map of tile i-1 only after tile i has been enqueued, like ChipPipeline does for chip batches.
     res = [torch.empty((H, W), dtype=torch.int8).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event(), torch.cuda.Event()]
-    for _ in range(max(2, warmup)):   # both upload slots of the engine exist before the clock starts (cudaMalloc synchronises)
-        IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw)
+    for i in range(max(2, warmup)):   # both upload slots and the result stream exist before the clock starts (cudaMalloc synchronises)
+        IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, out_host=res[i & 1], **kw)
     barrier()
     t0 = time.perf_counter()
     for i in range(steps):
         k = i & 1
         if i >= 2:
             done[k].synchronize()      # the buffer's previous map has reached the host (a consumer would read it here)
-        res[k].copy_(IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, **kw), non_blocking=True)
-        done[k].record()
+        IU.sliding_window_inference_sharded(pinned_tile, model, rank, world, copy=False, out_host=res[k], **kw)
+        done[k] = IU.tile_result_event()   # the map travels on the engine's result stream while the next tile is computed
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     res = res[(steps - 1) & 1]

@@ -318,6 +318,9 @@ class TileEngine:
         self._in_ready = [torch.cuda.Event(), torch.cuda.Event()]
         self._in_free = [torch.cuda.Event(), torch.cuda.Event()]
         self._staged = None     # slot whose consumption by the compute stream has to be marked (in_free)
+        self._d2h_stream = None  # result copies to the host (out_host=) run here
+        self._d2h_done = None    # event of a host copy that still reads the result buffer
+        self._result_event = None
         n_own = o1 - o0
         self.n_calls = max(1, -(-n_own // self.batch_size)) if n_own else 0
         self.per_call = max(1, -(-n_own // self.n_calls)) if n_own else 0
@@ -383,9 +386,12 @@ class TileEngine:
 
     # -- one tile ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def run(self, hls_tile, fmask=None, gather: bool = True) -> torch.Tensor:
+    def run(self, hls_tile, fmask=None, gather: bool = True, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """int8 class map: the whole [H, W] map when ``gather`` (all ranks end up with it), else this rank's stripe
-        [y1-y0, W].  The returned tensor is a VIEW of the engine's buffer: valid until the next ``run``."""
+        [y1-y0, W].  The returned tensor is a VIEW of the engine's buffer: valid until the next ``run``.
+        ``out_host`` (pinned int8 tensor of the result's shape): the result is also copied to the host on a stream of
+        its own, so the copy of tile i travels while tile i+1 is computed; ``result_event()`` completes when it has
+        arrived.  The engine does not overwrite its result buffer before that copy has read it."""
         with torch.cuda.device(self.device):
             mark = self._mark if self.timing else (lambda name: None)
             if self.timing:
@@ -420,6 +426,9 @@ class TileEngine:
             for req in reqs:
                 req.wait()
             mark("window-logit exchange (+ nodata map)")
+            if self._d2h_done is not None:   # the previous tile's host copy still reads the result buffer
+                torch.cuda.current_stream(self.device).wait_event(self._d2h_done)
+                self._d2h_done = None
             if rows:
                 n0, n1 = self.need
                 ops.stitch(self.logits[n0 - self.u0:n1 - self.u0], self.ys, self.xs, self.H, self.W, y0=self.y0,
@@ -427,10 +436,33 @@ class TileEngine:
                            origins=self.origins, out=self.out)
             mark("stitch")
             if not gather or self.world == 1:
-                return self.out
-            full = self._gather()
-            mark("stripe all-gather")
-            return full
+                res = self.out
+            else:
+                res = self._gather()
+                mark("stripe all-gather")
+            if out_host is not None:
+                self._to_host(res, out_host)
+            return res
+
+    def _to_host(self, res: torch.Tensor, out_host: torch.Tensor) -> None:
+        if not (isinstance(out_host, torch.Tensor) and out_host.is_pinned() and out_host.dtype == res.dtype
+                and tuple(out_host.shape) == tuple(res.shape) and out_host.is_contiguous()):
+            raise ValueError(f"out_host must be a pinned contiguous {res.dtype} tensor of shape {tuple(res.shape)}")
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(ready)
+            out_host.copy_(res, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._d2h_stream)
+        self._d2h_done = done
+        self._result_event = done
+
+    def result_event(self) -> Optional[torch.cuda.Event]:
+        """Event of the last ``out_host`` copy (``.synchronize()`` before reading the host buffer)."""
+        return self._result_event
 
     # -- optional device-side phase timing (tools/tile_phases.py) ---------------------------------------------------
     timing = False
@@ -532,12 +564,13 @@ def sliding_window_inference(hls_tile, model: PrithviSeg, window_size=(224, 224)
 
 @torch.no_grad()
 def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, world_size: int,
-                                     halo_recompute: bool = False, copy: bool = True, **kw):
+                                     halo_recompute: bool = False, copy: bool = True, out_host=None, **kw):
     """One process per GPU: every rank runs the model on its share of the windows, the windows a stripe needs from
     other ranks are exchanged over NCCL send/recv, each rank stitches its output row stripe, and the int8 stripes
     are all-gathered in place.  ``halo_recompute=True`` is the collective-free alternative (every rank recomputes
     the windows that touch its stripe).  Either way the result is bit-identical to one GPU.  Returns [H, W] int8 on
-    the device (``copy=False``: a view of the engine's buffer, overwritten by the next tile)."""
+    the device (``copy=False``: a view of the engine's buffer, overwritten by the next tile).  ``out_host``: a pinned
+    int8 [H, W] tensor that also receives the map, copied on a side stream (``tile_result_event()`` tells when)."""
     kw = dict(kw)
     window_size = kw.pop("window_size", (224, 224))
     stride, batch_size = kw.pop("stride", 224), kw.pop("batch_size", 32)
@@ -559,8 +592,18 @@ def sliding_window_inference_sharded(hls_tile, model: PrithviSeg, rank: int, wor
     if kw:
         raise TypeError(f"unexpected arguments {sorted(kw)}")
     eng = tile_engine(hls_tile, model, win, stride, batch_size, dev, **ekw)
-    out = eng.run(hls_tile, fmask=fmask, gather=True)
+    out = eng.run(hls_tile, fmask=fmask, gather=True, out_host=out_host)
+    global _LAST_ENGINE
+    _LAST_ENGINE = eng
     return out.clone() if copy else out
+
+
+_LAST_ENGINE: Optional[TileEngine] = None
+
+
+def tile_result_event() -> Optional[torch.cuda.Event]:
+    """Completion event of the ``out_host`` copy of the last ``sliding_window_inference_sharded`` call."""
+    return None if _LAST_ENGINE is None else _LAST_ENGINE.result_event()
 
 
 # --------------------------------------------------------------------------- host <-> device pipeline

@@ -147,6 +147,22 @@ def test_tile_engine_host_rows_and_device_tile_agree(cuda_dev):
                 assert torch.equal(part, full[y0:y1])
     # world_size 1 through the sharded entry (in-place gather buffer, no collective)
     assert torch.equal(IU.sliding_window_inference_sharded(pinned, m, 0, 1, **kw), full)
+    # a stream of DIFFERENT tiles with the result copied to pinned host buffers on the engine's side stream: every host
+    # map equals the map of its own tile (the engine must not overwrite its result buffer under a copy in flight)
+    tiles = [tile, np.roll(tile, 97, axis=2).copy(), np.flip(tile, axis=1).copy(), tile]
+    want = [IU.sliding_window_inference(torch.from_numpy(t).to(cuda_dev), m, return_tensor=True, **kw).cpu() for t in tiles]
+    assert not torch.equal(want[0], want[1]) and not torch.equal(want[0], want[2])
+    pins = [torch.from_numpy(t).pin_memory() for t in tiles]
+    hosts = [torch.empty((H, W), dtype=torch.int8).pin_memory() for _ in tiles]
+    events = []
+    for t_pin, h in zip(pins, hosts):
+        IU.sliding_window_inference_sharded(t_pin, m, 0, 1, copy=False, out_host=h, **kw)
+        events.append(IU.tile_result_event())
+    for ev, h, w_ in zip(events, hosts, want):
+        ev.synchronize()
+        assert torch.equal(h, w_)
+    with pytest.raises(ValueError):
+        IU.sliding_window_inference_sharded(pinned, m, 0, 1, out_host=torch.empty((H, W), dtype=torch.int8), **kw)
     # optional per-phase device timing (tools/tile_phases.py): same result, one positive duration per phase
     engines = [e for e in IU._ENGINES.values() if e.model is m]
     for e in engines:

@@ -36,18 +36,19 @@ for stride in [int(a) for a in sys.argv[1:]] or [112, 224]:
         for d2h in (False, True):
             res = [torch.empty((H, W), dtype=torch.int8).pin_memory() for _ in range(2)]
             done = [torch.cuda.Event(), torch.cuda.Event()]
-            for _ in range(3):
-                IU.sliding_window_inference_sharded(src, model, rank, world, copy=False, **kw)
+            for i in range(3):
+                IU.sliding_window_inference_sharded(src, model, rank, world, copy=False, out_host=res[i & 1] if d2h else None, **kw)
             barrier()
             t0 = time.perf_counter()
             for i in range(steps):
                 k = i & 1
                 if i >= 2:
                     done[k].synchronize()
-                out = IU.sliding_window_inference_sharded(src, model, rank, world, copy=False, **kw)
+                IU.sliding_window_inference_sharded(src, model, rank, world, copy=False, out_host=res[k] if d2h else None, **kw)
                 if d2h:
-                    res[k].copy_(out, non_blocking=True)
-                done[k].record()
+                    done[k] = IU.tile_result_event()
+                else:
+                    done[k].record()
             torch.cuda.synchronize()
             dt = torch.tensor([(time.perf_counter() - t0) / steps * 1e3], device=dev)
             if world > 1:
