@@ -19,6 +19,12 @@
 //                                (bf16/f32 store, f32 residual read, pos-embed read) is a full 128-byte
 //                                line per row instead of 32 scattered 16-byte pieces
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// The MMA warp is one serial instruction stream and sets the pace of every short tile (tools/gemm_trace.py): the tile
+// decode has no divisions, the accumulate flag of a UMMA is a literal or a warp-uniform value (no R2UR chain per
+// UTCHMMA), the last K block of a K that is not a multiple of 64 travels as a 16- / 32-column box (SWIZZLE_32B / 64B),
+// and where a unit is a single K block of a narrow tile the whole tile's units share one ring slot.
+// The in-place f32 residual (x += A W^T + b) leaves as bulk tensor REDUCTIONS of the per-warp staging tiles
+// (cp.reduce.async.bulk.tensor .add.f32: the L2 adds, the SM neither loads x nor stores the sum).
 //
 // The same kernel runs the segmentation head as an implicit GEMM with NO im2col: activations
 // live in a zero-bordered "padded-flat" NHWC layout [B*(H+2)*(W+2), C], so a 3x3 tap (dy,dx)
