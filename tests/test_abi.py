@@ -111,10 +111,24 @@ def test_committed_bench_lines_follow_the_contract():
         assert {"value", "unit", "cores", "kind", "sample"} <= set(head["cpu_baseline"])   # the driver's N = 1 line
         assert head["roofline"]["bound"] == "tensor" and 0 < head["roofline"]["frac"] < 1
     # round 2: parity of the timed batch and the tile section travel in the same line
-    for name in ("r02_bench_chips_v1.json", "r02_bench_chips_v1_8gpu.json"):
+    for name in ("r02_bench_chips_v1.json", "r02_bench_chips_v1_2gpu.json", "r02_bench_chips_v1_4gpu.json",
+                 "r02_bench_chips_v1_8gpu.json"):
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         assert d["parity"]["ok"] and d["parity"]["max_abs"] < d["parity"]["tol"] and d["parity"]["timed_batch_argmax_identical"]
         assert d["tile"]["ok"] and {"stride112", "stride224"} <= set(d["tile"])
         assert min(d["tile"]["stride112"]["class_hist"]) > 0                     # nodata, class 0 and class 1 all present
         if d["n_gpus"] > 1:
             assert d["tile"]["stride112"]["bit_identical_to_single_gpu"] == {"window_exchange": True, "halo_recompute": True}
+            assert d["tile"]["stride224"]["bit_identical_to_single_gpu"] == {"window_exchange": True, "halo_recompute": True}
+        assert d["chips_v2_300m"]["value"] > 0 and d["forward_path"]["cuda_graph_replay"]
+
+
+def test_roofline_traffic_comes_from_the_committed_launch_list():
+    """bench.py's roofline.traffic is read from profiles/r02_launches_bench_step.csv (the ncu launch list of the same
+    command): the file is there, parses, and gives a per-launch DRAM figure of the right order (100 MB - 1 GB)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    assert os.path.exists(os.path.join(ROOT, "profiles", "r02_launches_bench_step.csv"))
+    t = bench.gemm_traffic_from_profile()
+    assert t is not None and 1e8 < t < 1e9
